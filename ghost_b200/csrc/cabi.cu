@@ -1,0 +1,307 @@
+// extern "C" boundary (include/ghost_cwt.h): plan management and dispatch.
+#include "plan.h"
+#include "common.cuh"
+#include <cstring>
+#include <new>
+
+namespace gcwt {
+
+static thread_local std::string g_last_error;
+static thread_local int64_t g_launches = 0;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+void count_launch(int n) { g_launches += n; }
+int64_t launches_so_far() { return g_launches; }
+
+int prof_begin(gcwt_plan* p, int kind, cudaStream_t st) {
+    if (!p->profile) return -1;
+    gcwt_plan::Span sp;
+    sp.kind = kind;
+    sp.launches = (int)g_launches;
+    if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return -1;
+    cudaEventRecord(sp.a, st);
+    p->spans.push_back(sp);
+    return (int)p->spans.size() - 1;
+}
+
+void prof_end(gcwt_plan* p, int idx, cudaStream_t st) {
+    if (idx < 0) return;
+    gcwt_plan::Span& sp = p->spans[idx];
+    sp.launches = (int)g_launches - sp.launches;
+    cudaEventRecord(sp.b, st);
+}
+
+static void prof_collect(gcwt_plan* p) {
+    for (auto& sp : p->spans) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            p->prof_ms[sp.kind] += ms;
+            p->prof_launches[sp.kind] += sp.launches;
+        }
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    p->spans.clear();
+}
+
+int ensure_workspace(gcwt_plan* p, size_t bytes) {
+    if (p->ws.bytes >= bytes) return GCWT_OK;
+    if (p->ws.ptr) { cudaFree(p->ws.ptr); p->ws.ptr = nullptr; p->ws.bytes = 0; }
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p->ws.ptr, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&p->ws.ptr, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("workspace allocation of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+        return GCWT_ERR_NOMEM;
+    }
+    p->ws.bytes = want;
+    return GCWT_OK;
+}
+
+int filter_response_device(int64_t L, int k_first, int n_terms, const double* terms_host, int64_t nfft,
+                           int64_t first_bin, int64_t n_bins, double* out_host);
+
+int morse_kernel_device(int64_t L, int k_first, int n_terms, const double* terms_host, double* out_host);
+
+static int check_exec_args(const gcwt_plan* plan, const void* x, int in_type, int64_t n_channels,
+                           int64_t n_samples, int64_t x_stride, const void* out) {
+    if (!plan) { set_error("plan is NULL"); return GCWT_ERR_ARG; }
+    if (!x || !out) { set_error("x/out is NULL"); return GCWT_ERR_ARG; }
+    if (in_type != GCWT_F32 && in_type != GCWT_F64) { set_error("in_type must be GCWT_F32 or GCWT_F64"); return GCWT_ERR_ARG; }
+    if (n_channels <= 0 || n_samples <= 0) { set_error("n_channels and n_samples must be positive"); return GCWT_ERR_ARG; }
+    if (n_channels > 65535) { set_error("at most 65535 channels per call"); return GCWT_ERR_ARG; }
+    if (x_stride < n_samples && n_channels > 1) { set_error("x_stride smaller than n_samples"); return GCWT_ERR_ARG; }
+    return GCWT_OK;
+}
+
+}  // namespace gcwt
+
+using namespace gcwt;
+
+extern "C" {
+
+int gcwt_version(void) { return GCWT_VERSION; }
+
+const char* gcwt_last_error(void) { return g_last_error.c_str(); }
+
+int64_t gcwt_launch_count(int32_t reset) {
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int gcwt_plan_create(gcwt_plan** out, const gcwt_plan_desc* d) {
+    if (!out || !d) { set_error("plan_create: NULL argument"); return GCWT_ERR_ARG; }
+    *out = nullptr;
+    if (d->n_scales <= 0 || !d->lengths || !d->k_first || !d->n_terms || !d->terms) {
+        set_error("plan_create: empty or NULL scale tables"); return GCWT_ERR_ARG;
+    }
+    if (d->compute_type != GCWT_F32 && d->compute_type != GCWT_F64) { set_error("plan_create: bad compute_type"); return GCWT_ERR_ARG; }
+    if (d->out_kind < GCWT_OUT_COMPLEX || d->out_kind > GCWT_OUT_POWER) { set_error("plan_create: bad out_kind"); return GCWT_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (this library has no CPU fallback)");
+        return GCWT_ERR_CUDA;
+    }
+    if (d->device < 0 || d->device >= ndev) { set_error("plan_create: bad device ordinal"); return GCWT_ERR_ARG; }
+    GCWT_CUDA_OK(cudaSetDevice(d->device));
+
+    gcwt_plan* p = new (std::nothrow) gcwt_plan();
+    if (!p) { set_error("out of host memory"); return GCWT_ERR_NOMEM; }
+    p->n_scales = d->n_scales;
+    p->compute_type = d->compute_type;
+    p->out_kind = d->out_kind;
+    p->device = d->device;
+    p->flags = d->flags;
+    p->band_tol = d->band_tol > 0 ? d->band_tol : 3e-7;
+    int off = 0;
+    for (int s = 0; s < d->n_scales; ++s) {
+        ScaleInfo sc;
+        sc.L = d->lengths[s];
+        sc.k_first = d->k_first[s];
+        sc.n_terms = d->n_terms[s];
+        sc.term_off = off;
+        sc.level = -2;
+        if (sc.L < 1 || sc.n_terms < 1 || sc.k_first < 0 || sc.k_first + sc.n_terms > sc.L) {
+            set_error("plan_create: inconsistent scale " + std::to_string(s));
+            delete p;
+            return GCWT_ERR_ARG;
+        }
+        off += sc.n_terms;
+        p->scales.push_back(sc);
+    }
+    p->terms.assign(d->terms, d->terms + off);
+
+    int rc = GCWT_OK;
+    if (p->compute_type == GCWT_F32) rc = fast_plan_build(p);
+    else for (int s = 0; s < p->n_scales; ++s) p->generic_ids.push_back(s);
+    if (rc == GCWT_OK) {
+        cudaError_t e = cudaMalloc((void**)&p->d_scales, sizeof(ScaleInfo) * p->n_scales);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_terms, sizeof(double) * p->terms.size());
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_scales, p->scales.data(), sizeof(ScaleInfo) * p->n_scales, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_terms, p->terms.data(), sizeof(double) * p->terms.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error(std::string("plan_create: ") + cudaGetErrorString(e)); rc = GCWT_ERR_CUDA; }
+    }
+    if (rc != GCWT_OK) { gcwt_plan_destroy(p); return rc; }
+    *out = p;
+    return GCWT_OK;
+}
+
+int gcwt_plan_destroy(gcwt_plan* p) {
+    if (!p) return GCWT_OK;
+    cudaSetDevice(p->device);
+    prof_collect(p);
+    fast_plan_free(p);
+    if (p->d_scales) cudaFree(p->d_scales);
+    if (p->d_terms) cudaFree(p->d_terms);
+    if (p->ws.ptr) cudaFree(p->ws.ptr);
+    if (p->d_means) cudaFree(p->d_means);
+    delete p;
+    return GCWT_OK;
+}
+
+int gcwt_profile_enable(gcwt_plan* p, int32_t on) {
+    if (!p) { set_error("profile_enable: NULL plan"); return GCWT_ERR_ARG; }
+    p->profile = on != 0;
+    return GCWT_OK;
+}
+
+int gcwt_profile_read(gcwt_plan* p, double* ms_out, int64_t* launches_out, int32_t reset) {
+    if (!p || !ms_out || !launches_out) { set_error("profile_read: NULL argument"); return GCWT_ERR_ARG; }
+    cudaSetDevice(p->device);
+    prof_collect(p);
+    for (int k = 0; k < GCWT_PROFILE_KINDS; ++k) {
+        ms_out[k] = p->prof_ms[k];
+        launches_out[k] = p->prof_launches[k];
+        if (reset) { p->prof_ms[k] = 0; p->prof_launches[k] = 0; }
+    }
+    return GCWT_OK;
+}
+
+int gcwt_plan_levels(const gcwt_plan* p, int32_t* levels_out) {
+    if (!p || !levels_out) { set_error("plan_levels: NULL argument"); return GCWT_ERR_ARG; }
+    for (int s = 0; s < p->n_scales; ++s) levels_out[s] = p->scales[s].level;
+    return GCWT_OK;
+}
+
+size_t gcwt_plan_workspace_bytes(const gcwt_plan* p) { return p ? p->ws.bytes : 0; }
+
+int gcwt_channel_means(const void* x, int32_t in_type, int64_t n_channels, int64_t n_samples,
+                       int64_t x_stride, double* means_dev, int32_t device, void* stream) {
+    if (!x || !means_dev) { set_error("channel_means: NULL argument"); return GCWT_ERR_ARG; }
+    if (in_type != GCWT_F32 && in_type != GCWT_F64) { set_error("channel_means: bad in_type"); return GCWT_ERR_ARG; }
+    GCWT_CUDA_OK(cudaSetDevice(device));
+    return means_launch(x, in_type, n_channels, n_samples, x_stride, means_dev, (cudaStream_t)stream);
+}
+
+int gcwt_execute(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_channels, int64_t n_samples,
+                 int64_t x_stride, int64_t halo_left, int64_t halo_right, const double* means,
+                 void* out, int64_t out_scale_stride, int64_t out_channel_stride, void* stream) {
+    int rc = check_exec_args(p, x, in_type, n_channels, n_samples, x_stride, out);
+    if (rc) return rc;
+    if (halo_left < 0 || halo_right < 0) { set_error("execute: negative halo"); return GCWT_ERR_ARG; }
+    GCWT_CUDA_OK(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const double* d_means = means;
+    if (!d_means) {
+        if (p->means_cap < n_channels) {
+            if (p->d_means) cudaFree(p->d_means);
+            p->d_means = nullptr; p->means_cap = 0;
+            GCWT_CUDA_OK(cudaMalloc((void**)&p->d_means, sizeof(double) * n_channels));
+            p->means_cap = n_channels;
+        }
+        const int sp = prof_begin(p, 0, st);
+        rc = means_launch(x, in_type, n_channels, n_samples, x_stride, p->d_means, st);
+        prof_end(p, sp, st);
+        if (rc) return rc;
+        d_means = p->d_means;
+    }
+    // the two drivers share one workspace: size it for the larger user up front is not
+    // needed because they run back to back on the same stream and each re-derives its
+    // layout from the base pointer; growing between them would free memory still in use,
+    // so run the generic part first only after synchronising a grown workspace.
+    if (p->compute_type == GCWT_F32 && !p->classes.empty()) {
+        rc = fast_execute(p, x, in_type, n_channels, n_samples, x_stride, halo_left, halo_right, d_means,
+                          out, out_scale_stride, out_channel_stride, st);
+        if (rc) return rc;
+        if (!p->generic_ids.empty()) GCWT_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    if (!p->generic_ids.empty()) {
+        const int sp = prof_begin(p, 3, st);
+        rc = generic_execute(p, p->generic_ids, x, in_type, n_channels, n_samples, x_stride, halo_left,
+                             halo_right, d_means, out, out_scale_stride, out_channel_stride, st);
+        prof_end(p, sp, st);
+        if (rc) return rc;
+    }
+    return GCWT_OK;
+}
+
+int gcwt_execute_host(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_channels,
+                      int64_t n_samples, int64_t x_stride, const double* means_host, void* out,
+                      int64_t out_scale_stride, int64_t out_channel_stride) {
+    int rc = check_exec_args(p, x, in_type, n_channels, n_samples, x_stride, out);
+    if (rc) return rc;
+    GCWT_CUDA_OK(cudaSetDevice(p->device));
+    const size_t in_el = in_type == GCWT_F32 ? 4 : 8;
+    size_t out_el = p->compute_type == GCWT_F32 ? 4 : 8;
+    if (p->out_kind == GCWT_OUT_COMPLEX) out_el *= 2;
+    // device staging uses dense strides
+    const int64_t d_s = n_samples, d_c = n_samples * p->n_scales;
+    void *d_x = nullptr, *d_out = nullptr;
+    double* d_means = nullptr;
+    cudaError_t e = cudaMalloc(&d_x, in_el * n_samples * n_channels);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_el * (size_t)d_c * n_channels);
+    if (e == cudaSuccess && means_host) e = cudaMalloc((void**)&d_means, sizeof(double) * n_channels);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (d_x) cudaFree(d_x);
+        if (d_out) cudaFree(d_out);
+        set_error(std::string("execute_host: device allocation failed: ") + cudaGetErrorString(e));
+        return GCWT_ERR_NOMEM;
+    }
+    rc = GCWT_OK;
+    e = cudaMemcpy2D(d_x, in_el * n_samples, x, in_el * x_stride, in_el * n_samples, n_channels, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && means_host) e = cudaMemcpy(d_means, means_host, sizeof(double) * n_channels, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error(std::string("execute_host: H2D failed: ") + cudaGetErrorString(e)); rc = GCWT_ERR_CUDA; }
+    if (rc == GCWT_OK)
+        rc = gcwt_execute(p, d_x, in_type, n_channels, n_samples, n_samples, 0, 0, d_means, d_out, d_s, d_c, nullptr);
+    if (rc == GCWT_OK) {
+        e = cudaDeviceSynchronize();
+        for (int64_t c = 0; c < n_channels && e == cudaSuccess; ++c)
+            e = cudaMemcpy2D((char*)out + out_el * c * out_channel_stride, out_el * out_scale_stride,
+                             (char*)d_out + out_el * c * d_c, out_el * d_s, out_el * n_samples, p->n_scales,
+                             cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error(std::string("execute_host: D2H failed: ") + cudaGetErrorString(e)); rc = GCWT_ERR_CUDA; }
+    }
+    cudaFree(d_x);
+    cudaFree(d_out);
+    if (d_means) cudaFree(d_means);
+    return rc;
+}
+
+int gcwt_filter_response(int64_t length, int32_t k_first, int32_t n_terms, const double* terms,
+                         int64_t n_fft, int64_t first_bin, int64_t n_bins, double* out_host,
+                         int32_t device) {
+    if (!terms || !out_host || length < 1 || n_terms < 1 || n_fft < length || n_bins < 1 || first_bin < 0) {
+        set_error("filter_response: bad argument"); return GCWT_ERR_ARG;
+    }
+    GCWT_CUDA_OK(cudaSetDevice(device));
+    return filter_response_device(length, k_first, n_terms, terms, n_fft, first_bin, n_bins, out_host);
+}
+
+int gcwt_morse_kernel(int64_t length, int32_t k_first, int32_t n_terms, const double* terms,
+                      double* out_host, int32_t device) {
+    if (!terms || !out_host || length < 1 || n_terms < 1 || k_first < 0) {
+        set_error("morse_kernel: bad argument"); return GCWT_ERR_ARG;
+    }
+    GCWT_CUDA_OK(cudaSetDevice(device));
+    return morse_kernel_device(length, k_first, n_terms, terms, out_host);
+}
+
+}  // extern "C"

@@ -1,0 +1,546 @@
+// fp32 fast path: half-band decimation pyramid + fused overlap-save kernels.
+//
+// One fused kernel per scale class does, for a chunk of the recording that stays in
+// shared memory: (1) forward FFT of the chunk, (2) multiply by each scale's exact filter
+// response (closed form of the reference's L-tap Morse kernel, see multiplier.cuh),
+// (3) inverse FFT per scale and (4) the |W| / |W|^2 / complex epilogue straight to the
+// output rows.  No wavelet bank of size scales x N and no intermediate spectrum ever
+// touches HBM (north-star kernels (1)-(3)).
+//
+// Wavelets are band-pass: a scale whose response lives below pi/(2 D) is computed from
+// the recording decimated by D = 2^level (zero-phase half-band cascade, exactly
+// compensated in the multiplier), so that every chunk needs only kBins = 256 spectrum
+// bins however long the kernel is (L reaches 236 760 taps at 30 kHz).  The inverse
+// transform back to the full sample rate is a 256*P-point FFT with 256 non-zero inputs:
+// output sample n = n1*P + n2 is the n1-th output of a 256-point FFT of the spectrum
+// times the phase ramp e^{2 pi i m n2 / (256 P)}.  Each lane of a warp owns one column
+// n2, so stores are contiguous runs across lanes.
+//
+// Replaces ghost/sigtools/convolution.py:63-87 (fastconv overlap-add), morseutils.py:
+// 115-151 (kernel synthesis) and transforms.py:142-143,202-204 (mean removal, abs).
+#include "plan.h"
+#include "common.cuh"
+#include "multiplier.cuh"
+#include <algorithm>
+#include <cmath>
+#include <map>
+
+namespace gcwt {
+
+constexpr int kMaxFastLevel = 14;       // chunk of 1024 << 14 samples: phases stay exact in fp32
+constexpr int kMaxFullScales = 64;
+constexpr double kMaxHaloFrac = 0.45;   // (L-1) / chunk must stay below this
+
+__constant__ double c_halfband[kHalfbandOdd];
+
+// ============================================================================ planner
+static double bessel_i0(double x) {
+    double sum = 1.0, term = 1.0;
+    const double q = x * x / 4.0;
+    for (int k = 1; k < 200; ++k) {
+        term *= q / ((double)k * (double)k);
+        sum += term;
+        if (term < 1e-18 * sum) break;
+    }
+    return sum;
+}
+
+static void design_halfband(double* odd /*kHalfbandOdd*/) {
+    const int T = kHalfbandT;
+    const double atten = 140.0;
+    const double beta = 0.1102 * (atten - 8.7);
+    const double i0b = bessel_i0(beta);
+    double sum = 0.0;
+    for (int k = 0; k < kHalfbandOdd; ++k) {
+        const int t = 2 * k + 1;
+        const double r = (double)t / (double)T;
+        const double win = bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - r * r))) / i0b;
+        const double x = M_PI * t / 2.0;
+        odd[k] = 0.5 * std::sin(x) / x * win;
+        sum += 2.0 * odd[k];
+    }
+    for (int k = 0; k < kHalfbandOdd; ++k) odd[k] *= 0.5 / sum;      // unit DC gain
+}
+
+static double halfband_gain(const double* odd, double theta) {
+    double g = 0.5;
+    for (int k = 0; k < kHalfbandOdd; ++k) g += 2.0 * odd[k] * std::cos((2 * k + 1) * theta);
+    return g;
+}
+
+// out-of-band energy test of one scale on the (1024 << level)-point grid
+static bool band_fits(const gcwt_plan* p, const ScaleInfo& sc, int level, double* g_out /*kBins or null*/) {
+    const int64_t nc = (int64_t)kChunkDec << level;
+    const double* X = p->terms.data() + sc.term_off;
+    double e_in = 0.0;
+    for (int m = 0; m < kBins; ++m) {
+        const double g = morse_response(m, nc, sc.L, sc.k_first, sc.n_terms, X);
+        if (g_out) g_out[m] = g;
+        e_in += g * g;
+    }
+    double e_tot = 0.0;
+    for (int t = 0; t < sc.n_terms; ++t) e_tot += X[t] * X[t];
+    e_tot *= (double)nc / (double)sc.L;
+    return (1.0 - e_in / e_tot) < p->band_tol * p->band_tol;
+}
+
+static int choose_level(const gcwt_plan* p, const ScaleInfo& sc) {
+    if (!(p->flags & GCWT_FLAG_FORCE_GENERIC)) {
+        int lo = kMinFastLevel;
+        while (lo <= kMaxFastLevel && (double)(sc.L - 1) > kMaxHaloFrac * (double)((int64_t)kChunkDec << lo)) ++lo;
+        int hi = std::min(kMaxFastLevel, ilog2_ceil(sc.L) + 1);
+        for (int lev = hi; lev >= lo; --lev)
+            if (band_fits(p, sc, lev, nullptr)) return lev;
+        if ((double)(sc.L - 1) <= kMaxHaloFrac * kFullN) return -1;
+    }
+    return -2;
+}
+
+static void class_geometry(FastClass& fc) {
+    const int64_t d = fc.level >= 0 ? (int64_t(1) << fc.level) : 1;
+    const int64_t align = std::max<int64_t>(d, 16);
+    fc.offset = ((fc.lmax / 2 + align - 1) / align) * align;
+    fc.hop = ((fc.nc_full - (fc.lmax - 1) / 2 - fc.offset) / align) * align;
+}
+
+int fast_plan_build(gcwt_plan* p) {
+    design_halfband(p->halfband_odd);
+    GCWT_CUDA_OK(cudaMemcpyToSymbol(c_halfband, p->halfband_odd, sizeof(double) * kHalfbandOdd));
+    std::map<int, std::vector<int>> by_level;
+    p->max_level = 0;
+    for (int s = 0; s < p->n_scales; ++s) {
+        ScaleInfo& sc = p->scales[s];
+        sc.level = choose_level(p, sc);
+        if (sc.level == -2) p->generic_ids.push_back(s);
+        else by_level[sc.level].push_back(s);
+        p->max_level = std::max(p->max_level, sc.level);
+    }
+    for (auto& kv : by_level) {
+        const int level = kv.first;
+        const std::vector<int>& ids = kv.second;
+        const int cap = level >= 0 ? kMaxClassScales : kMaxFullScales;
+        for (size_t i0 = 0; i0 < ids.size(); i0 += cap) {
+            FastClass fc;
+            fc.level = level;
+            fc.nc_full = level >= 0 ? ((int64_t)kChunkDec << level) : kFullN;
+            fc.scale_ids.assign(ids.begin() + i0, ids.begin() + std::min(ids.size(), i0 + cap));
+            fc.lmax = 1;
+            for (int id : fc.scale_ids) fc.lmax = std::max(fc.lmax, p->scales[id].L);
+            class_geometry(fc);
+            if (fc.hop <= 0) { set_error("planner: non-positive hop"); return GCWT_ERR_ARG; }
+            const int nb = level >= 0 ? kBins : kFullN;
+            const int ns = (int)fc.scale_ids.size();
+            std::vector<float2> tab((size_t)ns * nb);
+            for (int i = 0; i < ns; ++i) {
+                const ScaleInfo& sc = p->scales[fc.scale_ids[i]];
+                const double* X = p->terms.data() + sc.term_off;
+                for (int m = 0; m < nb; ++m) {
+                    double g = morse_response(m, fc.nc_full, sc.L, sc.k_first, sc.n_terms, X);
+                    if (level >= 0) {
+                        const double w = 2.0 * M_PI * (double)m / (double)fc.nc_full;
+                        for (int st = 0; st < level; ++st) g /= halfband_gain(p->halfband_odd, w * (double)(1 << st));
+                        g /= (double)kChunkDec;
+                    } else {
+                        g /= (double)kFullN;
+                    }
+                    double re = g, im = 0.0;
+                    if ((sc.L & 1) == 0) {
+                        const double ph = -M_PI * (double)m / (double)fc.nc_full;
+                        re = g * std::cos(ph);
+                        im = g * std::sin(ph);
+                    }
+                    tab[(size_t)i * nb + m] = make_float2((float)re, (float)im);
+                }
+            }
+            GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_table, sizeof(float2) * tab.size()));
+            GCWT_CUDA_OK(cudaMemcpy(fc.d_table, tab.data(), sizeof(float2) * tab.size(), cudaMemcpyHostToDevice));
+            GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_scale_ids, sizeof(int32_t) * ns));
+            GCWT_CUDA_OK(cudaMemcpy(fc.d_scale_ids, fc.scale_ids.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
+            p->classes.push_back(fc);
+        }
+    }
+    return GCWT_OK;
+}
+
+void fast_plan_free(gcwt_plan* p) {
+    for (auto& fc : p->classes) {
+        if (fc.d_table) cudaFree(fc.d_table);
+        if (fc.d_scale_ids) cudaFree(fc.d_scale_ids);
+    }
+    p->classes.clear();
+}
+
+// ============================================================================ pyramid
+// out[i] = 0.5 in[2i] + sum_k h[2k+1] (in[2i-(2k+1)] + in[2i+(2k+1)]), zero outside the
+// readable range of `in`.  Level 1 reads the raw recording and removes the mean.
+constexpr int kPyrTile = 512;   // outputs per block
+
+template <typename TIn, bool FIRST>
+__global__ void __launch_bounds__(256)
+pyramid_kernel(const TIn* __restrict__ in, int64_t in_stride, int64_t in_lo, int64_t in_hi,
+               const double* __restrict__ means, float* __restrict__ out, int64_t out_stride,
+               int64_t out_lo, int64_t out_len) {
+    __shared__ float tile[2 * kPyrTile + 2 * kHalfbandT + 2];
+    const int c = blockIdx.y;
+    const int64_t i0 = out_lo + (int64_t)blockIdx.x * kPyrTile;     // first output index of the block
+    const int64_t u0 = 2 * i0 - kHalfbandT;                         // first input index needed
+    const TIn* src = in + (int64_t)c * in_stride - (FIRST ? 0 : in_lo);   // level arrays start at in_lo
+    const double mu = FIRST ? means[c] : 0.0;
+    for (int k = threadIdx.x; k < 2 * kPyrTile + 2 * kHalfbandT; k += blockDim.x) {
+        const int64_t u = u0 + k;
+        float v = 0.f;
+        if (u >= in_lo && u < in_hi) v = FIRST ? (float)((double)src[u] - mu) : (float)src[u];
+        tile[k] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < kPyrTile; j += blockDim.x) {
+        const int64_t i = i0 + j;
+        if (i - out_lo >= out_len) break;
+        const int ctr = 2 * j + kHalfbandT;
+        double acc = 0.5 * (double)tile[ctr];
+#pragma unroll
+        for (int k = 0; k < kHalfbandOdd; ++k)
+            acc += c_halfband[k] * ((double)tile[ctr - (2 * k + 1)] + (double)tile[ctr + (2 * k + 1)]);
+        out[(int64_t)c * out_stride + (i - out_lo)] = (float)acc;
+    }
+}
+
+// ============================================================================ fused kernels
+struct FusedParams {
+    const void* src;          // banded: float level array (origin src_lo); full: raw recording
+    int64_t src_stride;       // elements between channels
+    int64_t src_lo, src_hi;   // readable index range [lo, hi) in source index units
+    const double* means;      // full only
+    int log2d;                // banded: log2 of the decimation factor
+    int p_cols;               // banded: P = nc_full / kBins (columns per chunk)
+    float inv_nc;             // 1 / nc_full
+    int64_t offset, hop, n_chunks, n;
+    int n_scales;
+    const int32_t* scale_ids;
+    const float2* table;
+    void* out;
+    int64_t s_stride, c_stride;
+    int iters;                // column blocks (16 columns each) per unit
+    int units_per_chunk;
+};
+
+template <int KIND>
+__device__ __forceinline__ void store_coeff(void* out, int64_t idx, float2 v) {
+    if (KIND == GCWT_OUT_COMPLEX) ((float2*)out)[idx] = v;
+    else if (KIND == GCWT_OUT_AMPLITUDE) ((float*)out)[idx] = sqrtf(v.x * v.x + v.y * v.y);
+    else ((float*)out)[idx] = v.x * v.x + v.y * v.y;
+}
+
+// In-place-ish radix-4 Stockham FFT in shared memory, forward sign, N = 4^PASSES points,
+// 256 threads.  Result lands in `a` when PASSES is even, in `b` when odd.
+template <int PASSES>
+__device__ __forceinline__ float2* smem_fft_forward(float2* a, float2* b) {
+    constexpr int N = 1 << (2 * PASSES);
+    constexpr int M = N / 4;
+    int ns = 1;
+#pragma unroll 1
+    for (int pass = 0; pass < PASSES; ++pass) {
+        for (int j = threadIdx.x; j < M; j += 256) {
+            const int k = j & (ns - 1);
+            float2 v0 = a[j], v1 = a[j + M], v2 = a[j + 2 * M], v3 = a[j + 3 * M];
+            if (ns > 1) {
+                const float ang = -2.0f * (float)k / (float)(ns * 4);
+                v1 = cmul(v1, expipi(ang));
+                v2 = cmul(v2, expipi(2.0f * ang));
+                v3 = cmul(v3, expipi(3.0f * ang));
+            }
+            dft4<-1>(v0, v1, v2, v3);
+            const int j0 = ((j - k) << 2) + k;
+            b[j0] = v0; b[j0 + ns] = v1; b[j0 + 2 * ns] = v2; b[j0 + 3 * ns] = v3;
+        }
+        __syncthreads();
+        float2* t = a; a = b; b = t;
+        ns <<= 2;
+    }
+    return a;
+}
+
+// ---------------------------------------------------------------------------- banded
+// smem: ex[2][4096] | Zs[kMaxClassScales][256] | Estep[256]
+constexpr size_t kBandedSmem = sizeof(float2) * (2 * 4096 + kMaxClassScales * kBins + kBins);
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 2)
+fused_banded_kernel(const FusedParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* ex = (float2*)smem_raw;
+    float2* Zs = ex + 2 * 4096;
+    float2* Estep = Zs + kMaxClassScales * kBins;
+
+    const int tid = threadIdx.x;
+    const int r = tid & 15;            // column within the block of 16
+    const int g = tid >> 4;            // m_lo in pass 1, n_lo in pass 2
+
+    int64_t b = blockIdx.x;
+    const int unit = (int)(b % prm.units_per_chunk); b /= prm.units_per_chunk;
+    const int64_t q = b % prm.n_chunks;
+    const int64_t c = b / prm.n_chunks;
+
+    const int64_t t0 = q * prm.hop - prm.offset;                 // full-rate index of chunk sample 0
+    // ---- (1) forward FFT of the decimated chunk ---------------------------------
+    {
+        const float* src = (const float*)prm.src + c * prm.src_stride - prm.src_lo;
+        const int64_t i0 = t0 >> prm.log2d;                      // exact: t0 is a multiple of D
+        for (int i = tid; i < kChunkDec; i += 256) {
+            const int64_t u = i0 + i;
+            float v = 0.f;
+            if (u >= prm.src_lo && u < prm.src_hi) v = src[u];
+            ex[i] = make_float2(v, 0.f);
+        }
+        __syncthreads();
+        float2* Y = smem_fft_forward<5>(ex, ex + kChunkDec);     // 1024 points
+        // ---- (2) multiply by every scale's response (bins 0..255) ---------------
+        const float2 y = Y[tid];
+        for (int s = 0; s < prm.n_scales; ++s) Zs[s * kBins + tid] = cmul(y, prm.table[s * kBins + tid]);
+        Estep[tid] = expipi(2.0f * (float)(tid * 16) * prm.inv_nc);
+    }
+    // per-thread constants
+    float2 tw[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tw[k] = expipi((float)(2 * g * k) * (1.0f / 256.0f));
+    const int col0 = unit * prm.iters * 16;
+    float2 R[16];
+    {
+        const int64_t n2 = col0 + r;
+        const int64_t mask = ((int64_t)prm.p_cols * kBins) - 1;  // nc_full - 1 (power of two)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int64_t e = ((int64_t)(g + 16 * i) * n2) & mask;
+            R[i] = expipi(2.0f * (float)e * prm.inv_nc);
+        }
+    }
+    __syncthreads();
+
+    const int iters = min(prm.iters, prm.p_cols / 16 - unit * prm.iters);
+    int buf = 0;
+    for (int it = 0; it < iters; ++it) {
+        const int n2 = col0 + it * 16 + r;
+        for (int s = 0; s < prm.n_scales; ++s) {
+            float2 a[16];
+            const float2* z = Zs + s * kBins + g;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = cmul(z[16 * i], R[i]);
+            dft16<+1>(a);
+            float2* e = ex + buf * 4096 + (g * 16) * 16 + r;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
+            __syncthreads();
+            const float2* e2 = ex + buf * 4096 + g * 16 + r;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
+            dft16<+1>(a);
+            // ---- (3) epilogue ---------------------------------------------------
+            const int64_t obase = c * prm.c_stride + (int64_t)prm.scale_ids[s] * prm.s_stride;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int64_t i = (int64_t)(g + 16 * k) * prm.p_cols + n2;   // chunk-local sample
+                const int64_t t = t0 + i;
+                if (i >= prm.offset && i < prm.offset + prm.hop && t < prm.n) store_coeff<KIND>(prm.out, obase + t, a[k]);
+            }
+            buf ^= 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) R[i] = cmul(R[i], Estep[g + 16 * i]);
+    }
+}
+
+// ---------------------------------------------------------------------------- full spectrum
+// smem: Yf[4096] | A[4096] | ex[4096]
+constexpr size_t kFullSmem = sizeof(float2) * 3 * 4096;
+
+template <typename TIn, int KIND>
+__global__ void __launch_bounds__(256, 2)
+fused_full_kernel(const FusedParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Yf = (float2*)smem_raw;
+    float2* A = Yf + kFullN;
+    float2* ex = A + kFullN;
+
+    const int tid = threadIdx.x;
+    const int r = tid & 15;
+    const int g = tid >> 4;
+    const int64_t q = blockIdx.x % prm.n_chunks;
+    const int64_t c = blockIdx.x / prm.n_chunks;
+    const int64_t t0 = q * prm.hop - prm.offset;
+
+    {
+        const TIn* src = (const TIn*)prm.src + c * prm.src_stride;
+        const double mu = prm.means[c];
+        for (int i = tid; i < kFullN; i += 256) {
+            const int64_t u = t0 + i;
+            float v = 0.f;
+            if (u >= prm.src_lo && u < prm.src_hi) v = (float)((double)src[u] - mu);
+            Yf[i] = make_float2(v, 0.f);
+        }
+        __syncthreads();
+        smem_fft_forward<6>(Yf, A);                              // even pass count: result in Yf
+    }
+    float2 tw[16], tw4k[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        tw[k] = expipi((float)(2 * g * k) * (1.0f / 256.0f));
+        tw4k[k] = expipi((float)(2 * tid * k) * (1.0f / 4096.0f));
+    }
+    for (int s = 0; s < prm.n_scales; ++s) {
+        float2 a[16];
+        // pre-pass: radix-16 over mu for spectrum bin m' = tid
+        const float2* tab = prm.table + (int64_t)s * kFullN + tid;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = cmul(Yf[tid + 256 * k], tab[256 * k]);
+        dft16<+1>(a);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) A[tid * 16 + (k ^ (tid & 15))] = cmul(a[k], tw4k[k]);
+        __syncthreads();
+        // pass 1 of the 256-point transforms (16 columns)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 16 + (r ^ g)];
+        dft16<+1>(a);
+        float2* e = ex + (g * 16) * 16 + r;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
+        __syncthreads();
+        const float2* e2 = ex + g * 16 + r;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
+        dft16<+1>(a);
+        const int64_t obase = c * prm.c_stride + (int64_t)prm.scale_ids[s] * prm.s_stride;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int64_t i = (int64_t)(g + 16 * k) * 16 + r;
+            const int64_t t = t0 + i;
+            if (i >= prm.offset && i < prm.offset + prm.hop && t < prm.n) store_coeff<KIND>(prm.out, obase + t, a[k]);
+        }
+        // no trailing barrier: the next scale's pre-pass writes A, whose readers all passed
+        // the second barrier above; its pass 1 writes ex only after the next first barrier,
+        // which every thread reaches after finishing the reads of ex just done.
+    }
+}
+
+// ============================================================================ driver
+struct LevelGeom { int64_t lo, hi, len, stride; float* ptr; };
+
+template <typename TIn>
+static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels, int64_t n,
+                    int64_t x_stride, int64_t halo_l, int64_t halo_r, const double* d_means,
+                    void* out, int64_t s_stride, int64_t c_stride, cudaStream_t st) {
+    // ---- pyramid geometry ---------------------------------------------------------
+    const int levels = std::max(p->max_level, 0);
+    std::vector<LevelGeom> lv(levels + 1);
+    lv[0].lo = -halo_l; lv[0].hi = n + halo_r;                    // [lo, hi)
+    size_t total = 0;
+    for (int j = 1; j <= levels; ++j) {
+        const int64_t plo = lv[j - 1].lo, phi = lv[j - 1].hi - 1; // inclusive
+        const int64_t lo = (int64_t)std::floor((double)(plo - kHalfbandT) / 2.0);
+        const int64_t hi = (int64_t)std::ceil((double)(phi + kHalfbandT) / 2.0);
+        lv[j].lo = lo; lv[j].hi = hi + 1; lv[j].len = hi - lo + 1;
+        lv[j].stride = (lv[j].len + 3) & ~int64_t(3);
+        total += (size_t)lv[j].stride * n_channels;
+    }
+    int rc = ensure_workspace(p, total * sizeof(float) + 256);
+    if (rc) return rc;
+    float* w = (float*)p->ws.ptr;
+    for (int j = 1; j <= levels; ++j) { lv[j].ptr = w; w += lv[j].stride * n_channels; }
+
+    const int sp_pyr = prof_begin(p, 0, st);
+    for (int j = 1; j <= levels; ++j) {
+        dim3 grid((unsigned)((lv[j].len + kPyrTile - 1) / kPyrTile), (unsigned)n_channels);
+        if (j == 1)
+            pyramid_kernel<TIn, true><<<grid, 256, 0, st>>>(x, x_stride, lv[0].lo, lv[0].hi, d_means, lv[1].ptr,
+                                                            lv[1].stride, lv[1].lo, lv[1].len);
+        else
+            pyramid_kernel<float, false><<<grid, 256, 0, st>>>(lv[j - 1].ptr, lv[j - 1].stride, lv[j - 1].lo,
+                                                               lv[j - 1].hi, nullptr, lv[j].ptr, lv[j].stride,
+                                                               lv[j].lo, lv[j].len);
+        count_launch();
+    }
+    prof_end(p, sp_pyr, st);
+    GCWT_CUDA_OK(cudaGetLastError());
+
+    // ---- fused kernels ---------------------------------------------------------------
+    for (const FastClass& fc : p->classes) {
+        const int sp = prof_begin(p, fc.level >= 0 ? 2 : 1, st);
+        FusedParams prm;
+        prm.means = d_means;
+        prm.offset = fc.offset; prm.hop = fc.hop; prm.n = n;
+        prm.n_chunks = (n + fc.hop - 1) / fc.hop;
+        prm.n_scales = (int)fc.scale_ids.size();
+        prm.scale_ids = fc.d_scale_ids;
+        prm.table = fc.d_table;
+        prm.out = out; prm.s_stride = s_stride; prm.c_stride = c_stride;
+        prm.inv_nc = 1.0f / (float)fc.nc_full;
+        if (fc.level >= 0) {
+            const LevelGeom& g = lv[fc.level];
+            prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
+            prm.log2d = fc.level;
+            prm.p_cols = (int)(fc.nc_full / kBins);
+            const int blocks = prm.p_cols / 16;
+            prm.iters = std::min(blocks, 16);
+            prm.units_per_chunk = (blocks + prm.iters - 1) / prm.iters;
+            const int64_t nblk = n_channels * prm.n_chunks * prm.units_per_chunk;
+            if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
+            switch (p->out_kind) {
+                case GCWT_OUT_COMPLEX:
+                    fused_banded_kernel<GCWT_OUT_COMPLEX><<<(unsigned)nblk, 256, kBandedSmem, st>>>(prm); break;
+                case GCWT_OUT_AMPLITUDE:
+                    fused_banded_kernel<GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kBandedSmem, st>>>(prm); break;
+                default:
+                    fused_banded_kernel<GCWT_OUT_POWER><<<(unsigned)nblk, 256, kBandedSmem, st>>>(prm); break;
+            }
+        } else {
+            prm.src = x; prm.src_stride = x_stride; prm.src_lo = -halo_l; prm.src_hi = n + halo_r;
+            prm.log2d = 0; prm.p_cols = 16; prm.iters = 1; prm.units_per_chunk = 1;
+            const int64_t nblk = n_channels * prm.n_chunks;
+            if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
+            switch (p->out_kind) {
+                case GCWT_OUT_COMPLEX:
+                    fused_full_kernel<TIn, GCWT_OUT_COMPLEX><<<(unsigned)nblk, 256, kFullSmem, st>>>(prm); break;
+                case GCWT_OUT_AMPLITUDE:
+                    fused_full_kernel<TIn, GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kFullSmem, st>>>(prm); break;
+                default:
+                    fused_full_kernel<TIn, GCWT_OUT_POWER><<<(unsigned)nblk, 256, kFullSmem, st>>>(prm); break;
+            }
+        }
+        count_launch();
+        prof_end(p, sp, st);
+    }
+    GCWT_CUDA_OK(cudaGetLastError());
+    return GCWT_OK;
+}
+
+static bool g_attr_done[64] = {false};
+
+template <typename TIn>
+static int set_smem_attrs() {
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_banded_kernel<GCWT_OUT_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_banded_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_banded_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_full_kernel<TIn, GCWT_OUT_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_full_kernel<TIn, GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_full_kernel<TIn, GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem));
+    return GCWT_OK;
+}
+
+int fast_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, int64_t n_samples,
+                 int64_t x_stride, int64_t halo_l, int64_t halo_r, const double* d_means, void* out,
+                 int64_t s_stride, int64_t c_stride, cudaStream_t st) {
+    const int slot = (p->device & 31) * 2 + (in_type == GCWT_F32 ? 0 : 1);
+    if (!g_attr_done[slot]) {
+        int rc = in_type == GCWT_F32 ? set_smem_attrs<float>() : set_smem_attrs<double>();
+        if (rc) return rc;
+        // constant memory is per device: (re)load the half-band taps
+        GCWT_CUDA_OK(cudaMemcpyToSymbol(c_halfband, p->halfband_odd, sizeof(double) * kHalfbandOdd));
+        g_attr_done[slot] = true;
+    }
+    if (in_type == GCWT_F32)
+        return fast_run<float>(p, (const float*)x, in_type, n_channels, n_samples, x_stride, halo_l, halo_r,
+                               d_means, out, s_stride, c_stride, st);
+    return fast_run<double>(p, (const double*)x, in_type, n_channels, n_samples, x_stride, halo_l, halo_r,
+                            d_means, out, s_stride, c_stride, st);
+}
+
+}  // namespace gcwt

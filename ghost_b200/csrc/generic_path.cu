@@ -1,0 +1,355 @@
+// Generic full-spectrum overlap-save path (global-memory Stockham FFT).
+//
+// Serves the fp64 plans (parity bar 1e-10 needs the two-sided spectrum of the exact
+// filter) and is the fp32 fallback for scales the fused kernels cannot take.  Replaces
+// fastconv_scipy's overlap-ADD (ghost/sigtools/convolution.py:63-87) by overlap-SAVE
+// with the kernel's transfer function evaluated in closed form on the device instead of
+// fft(kernel, n) per block (convolution.py:75).
+#include "plan.h"
+#include "common.cuh"
+#include "multiplier.cuh"
+#include <algorithm>
+
+namespace gcwt {
+
+// ----------------------------------------------------------------------------- means
+template <typename TIn>
+__global__ void mean_partial_kernel(const TIn* __restrict__ x, int64_t n, int64_t stride,
+                                    double* __restrict__ partial) {
+    const int c = blockIdx.y, nb = gridDim.x;
+    const TIn* xc = x + (int64_t)c * stride;
+    const int64_t per = (n + nb - 1) / nb;
+    const int64_t lo = (int64_t)blockIdx.x * per;
+    const int64_t hi = min(n, lo + per);
+    double acc = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += (double)xc[i];
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(int64_t)c * nb + blockIdx.x] = sh[0];
+}
+
+__global__ void mean_final_kernel(const double* __restrict__ partial, int nb, int64_t n,
+                                  double* __restrict__ means, int n_channels) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_channels) return;
+    double acc = 0.0;
+    for (int i = 0; i < nb; ++i) acc += partial[(int64_t)c * nb + i];
+    means[c] = acc / (double)n;
+}
+
+int means_launch(const void* x, int in_type, int64_t n_channels, int64_t n_samples,
+                 int64_t x_stride, double* d_means, cudaStream_t st) {
+    if (n_channels <= 0 || n_samples <= 0) { set_error("means: empty input"); return GCWT_ERR_ARG; }
+    int nb = (int)std::min<int64_t>(512, (n_samples + 4095) / 4096);
+    if (nb < 1) nb = 1;
+    double* partial = nullptr;
+    GCWT_CUDA_OK(cudaMallocAsync((void**)&partial, sizeof(double) * nb * n_channels, st));
+    dim3 grid(nb, (unsigned)n_channels);
+    if (in_type == GCWT_F32)
+        mean_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, n_samples, x_stride, partial);
+    else
+        mean_partial_kernel<double><<<grid, 256, 0, st>>>((const double*)x, n_samples, x_stride, partial);
+    mean_final_kernel<<<(unsigned)((n_channels + 127) / 128), 128, 0, st>>>(partial, nb, n_samples, d_means,
+                                                                            (int)n_channels);
+    count_launch(2);
+    GCWT_CUDA_OK(cudaGetLastError());
+    GCWT_CUDA_OK(cudaFreeAsync(partial, st));
+    return GCWT_OK;
+}
+
+// ----------------------------------------------------------------------------- load
+template <typename TIn, typename T>
+__global__ void generic_load_kernel(const TIn* __restrict__ x, int64_t x_stride, int64_t n,
+                                    int64_t halo_l, int64_t halo_r, const double* __restrict__ means,
+                                    typename cplx_of<T>::type* __restrict__ dst, int nfft,
+                                    int64_t hop, int64_t offset, int64_t item0, int64_t n_chunks) {
+    const int64_t item = item0 + blockIdx.y;
+    const int64_t c = item / n_chunks, q = item % n_chunks;
+    const int64_t t0 = q * hop - offset;
+    const double mu = means[c];
+    const TIn* xc = x + c * x_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nfft; i += gridDim.x * blockDim.x) {
+        const int64_t t = t0 + i;
+        double v = 0.0;
+        if (t >= -halo_l && t < n + halo_r) v = (double)xc[t] - mu;
+        dst[(int64_t)blockIdx.y * nfft + i] = mk<T>((T)v, (T)0);
+    }
+}
+
+// ----------------------------------------------------------------------------- FFT pass
+// One radix-R Stockham autosort pass over `batch` transforms of length n.
+template <typename T, int R, int SIGN>
+__global__ void stockham_pass_kernel(const typename cplx_of<T>::type* __restrict__ in,
+                                     typename cplx_of<T>::type* __restrict__ out, int n, int ns) {
+    typedef typename cplx_of<T>::type C;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = n / R;
+    if (j >= m) return;
+    const int64_t base = (int64_t)blockIdx.y * n;
+    const int k = j % ns;
+    C v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = in[base + j + (int64_t)r * m];
+    if (ns > 1) {
+        const int span = ns * R;
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            const int e = (int)(((int64_t)r * k) % span);
+            C w = expipi((T)(SIGN * 2) * (T)e / (T)span);
+            v[r] = cmul(v[r], w);
+        }
+    }
+    small_dft<R, SIGN, C>::run(v);
+    const int64_t j0 = (int64_t)(j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[base + j0 + (int64_t)r * ns] = v[r];
+}
+
+template <typename T, int SIGN>
+static void fft_batched(typename cplx_of<T>::type*& a, typename cplx_of<T>::type*& b, int n, int batch,
+                        cudaStream_t st) {
+    // result ends up in `a` (pointers are swapped as passes go)
+    int lg = ilog2_ceil(n);
+    int ns = 1;
+    while (lg > 0) {
+        int r = lg >= 4 ? 16 : (1 << lg);
+        const int m = n / r;
+        dim3 grid((m + 127) / 128, batch);
+        switch (r) {
+            case 16: stockham_pass_kernel<T, 16, SIGN><<<grid, 128, 0, st>>>(a, b, n, ns); break;
+            case 8:  stockham_pass_kernel<T, 8, SIGN><<<grid, 128, 0, st>>>(a, b, n, ns); break;
+            case 4:  stockham_pass_kernel<T, 4, SIGN><<<grid, 128, 0, st>>>(a, b, n, ns); break;
+            default: stockham_pass_kernel<T, 2, SIGN><<<grid, 128, 0, st>>>(a, b, n, ns); break;
+        }
+        count_launch();
+        std::swap(a, b);
+        ns *= r;
+        lg -= (r == 16 ? 4 : lg);
+    }
+}
+
+// ----------------------------------------------------------------------------- response
+// H_s on the n-point grid, scaled by 1/n.  Kernel (2)'s multiplier, evaluated in registers.
+template <typename T>
+__global__ void generic_response_kernel(const ScaleInfo* __restrict__ scales,
+                                        const double* __restrict__ terms,
+                                        const int* __restrict__ ids, int nfft,
+                                        typename cplx_of<T>::type* __restrict__ H) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nfft) return;
+    const ScaleInfo sc = scales[ids[blockIdx.y]];
+    double g = morse_response(j, nfft, sc.L, sc.k_first, sc.n_terms, terms + sc.term_off);
+    g /= (double)nfft;
+    double re = g, im = 0.0;
+    if ((sc.L & 1) == 0) {                       // half-sample delay of the even-L kernel
+        double s, c;
+        sincospi(-(double)j / (double)nfft, &s, &c);
+        re = g * c;
+        im = g * s;
+    }
+    H[(int64_t)blockIdx.y * nfft + j] = mk<T>((T)re, (T)im);
+}
+
+template <typename T>
+__global__ void generic_multiply_kernel(const typename cplx_of<T>::type* __restrict__ Y,
+                                        const typename cplx_of<T>::type* __restrict__ H,
+                                        typename cplx_of<T>::type* __restrict__ Z, int nfft, int sb) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nfft) return;
+    const int s = blockIdx.y, ib = blockIdx.z;
+    Z[((int64_t)ib * sb + s) * nfft + j] = cmul(Y[(int64_t)ib * nfft + j], H[(int64_t)s * nfft + j]);
+}
+
+// ----------------------------------------------------------------------------- epilogue
+template <typename T, int KIND>
+__global__ void generic_epilogue_kernel(const typename cplx_of<T>::type* __restrict__ Z, int nfft,
+                                        int64_t item0, int64_t n_chunks, int64_t hop, int64_t offset,
+                                        int64_t n, const int* __restrict__ ids, int sb, void* out,
+                                        int64_t s_stride, int64_t c_stride) {
+    typedef typename cplx_of<T>::type C;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hop) return;
+    const int s = blockIdx.y, ib = blockIdx.z;
+    const int64_t item = item0 + ib;
+    const int64_t c = item / n_chunks, q = item % n_chunks;
+    const int64_t t = q * hop + i;
+    if (t >= n) return;
+    const C v = Z[((int64_t)ib * sb + s) * nfft + offset + i];
+    const int64_t o = c * c_stride + (int64_t)ids[s] * s_stride + t;
+    if (KIND == GCWT_OUT_COMPLEX) ((C*)out)[o] = v;
+    else if (KIND == GCWT_OUT_AMPLITUDE) ((T*)out)[o] = sqrt(v.x * v.x + v.y * v.y);
+    else ((T*)out)[o] = v.x * v.x + v.y * v.y;
+}
+
+// ----------------------------------------------------------------------------- driver
+template <typename TIn, typename T>
+static int generic_run(gcwt_plan* p, const std::vector<int>& ids, const TIn* x, int64_t n_channels,
+                       int64_t n, int64_t x_stride, int64_t halo_l, int64_t halo_r,
+                       const double* d_means, void* out, int64_t s_stride, int64_t c_stride,
+                       cudaStream_t st) {
+    typedef typename cplx_of<T>::type C;
+    const int ns = (int)ids.size();
+    int64_t lmax = 1;
+    for (int id : ids) lmax = std::max<int64_t>(lmax, p->scales[id].L);
+    // chunk geometry: one chunk when the whole segment fits a 2^20-point transform
+    int64_t nfft;
+    if (n + lmax - 1 <= (int64_t(1) << 20)) nfft = int64_t(1) << ilog2_ceil(n + lmax - 1);
+    else nfft = std::max<int64_t>(int64_t(1) << 17, int64_t(1) << ilog2_ceil(4 * lmax));
+    if (nfft > (int64_t(1) << 26)) { set_error("generic path: kernel too long"); return GCWT_ERR_UNSUPPORTED; }
+    if (nfft < 16) nfft = 16;
+    const int64_t offset = lmax / 2;
+    const int64_t hop = nfft - (lmax - 1);
+    const int64_t n_chunks = (n + hop - 1) / hop;
+    const int64_t n_items = n_channels * n_chunks;
+
+    const size_t row = (size_t)nfft * sizeof(C);
+    const size_t budget = (size_t)1 << 30;
+    int ib = (int)std::min<int64_t>(n_items, 4);
+    int sb = (int)std::min<int64_t>(ns, std::max<int64_t>(1, (int64_t)(budget / (2 * row * ib))));
+    sb = std::min(sb, 1024);
+    // layout: Y[ib] | H[sb] | Za[ib*sb] | Zb[ib*sb] | ids[ns] | Yscratch[ib]
+    const size_t need = row * ((size_t)ib * 2 + sb + 2 * (size_t)ib * sb) + sizeof(int) * ns + 256;
+    int rc = ensure_workspace(p, need);
+    if (rc) return rc;
+    char* w = (char*)p->ws.ptr;
+    C* Y = (C*)w;                 w += row * ib;
+    C* Y2 = (C*)w;                w += row * ib;
+    C* H = (C*)w;                 w += row * sb;
+    C* Za = (C*)w;                w += row * (size_t)ib * sb;
+    C* Zb = (C*)w;                w += row * (size_t)ib * sb;
+    int* d_ids = (int*)w;
+    GCWT_CUDA_OK(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+
+    const int tpb = 256;
+    const unsigned gx = (unsigned)((nfft + tpb - 1) / tpb);
+    for (int s0 = 0; s0 < ns; s0 += sb) {
+        const int sbn = std::min(sb, ns - s0);
+        generic_response_kernel<T><<<dim3(gx, sbn), tpb, 0, st>>>(p->d_scales, p->d_terms, d_ids + s0,
+                                                                  (int)nfft, H);
+        count_launch();
+        for (int64_t i0 = 0; i0 < n_items; i0 += ib) {
+            const int ibn = (int)std::min<int64_t>(ib, n_items - i0);
+            generic_load_kernel<TIn, T><<<dim3(std::min(gx, 1024u), ibn), tpb, 0, st>>>(
+                x, x_stride, n, halo_l, halo_r, d_means, Y, (int)nfft, hop, offset, i0, n_chunks);
+            count_launch();
+            C* ya = Y; C* yb = Y2;
+            fft_batched<T, -1>(ya, yb, (int)nfft, ibn, st);
+            generic_multiply_kernel<T><<<dim3(gx, sbn, ibn), tpb, 0, st>>>(ya, H, Za, (int)nfft, sbn);
+            count_launch();
+            C* za = Za; C* zb = Zb;
+            fft_batched<T, +1>(za, zb, (int)nfft, ibn * sbn, st);
+            dim3 ge((unsigned)((hop + tpb - 1) / tpb), sbn, ibn);
+            switch (p->out_kind) {
+                case GCWT_OUT_COMPLEX:
+                    generic_epilogue_kernel<T, GCWT_OUT_COMPLEX><<<ge, tpb, 0, st>>>(
+                        za, (int)nfft, i0, n_chunks, hop, offset, n, d_ids + s0, sbn, out, s_stride, c_stride);
+                    break;
+                case GCWT_OUT_AMPLITUDE:
+                    generic_epilogue_kernel<T, GCWT_OUT_AMPLITUDE><<<ge, tpb, 0, st>>>(
+                        za, (int)nfft, i0, n_chunks, hop, offset, n, d_ids + s0, sbn, out, s_stride, c_stride);
+                    break;
+                default:
+                    generic_epilogue_kernel<T, GCWT_OUT_POWER><<<ge, tpb, 0, st>>>(
+                        za, (int)nfft, i0, n_chunks, hop, offset, n, d_ids + s0, sbn, out, s_stride, c_stride);
+                    break;
+            }
+            count_launch();
+        }
+    }
+    GCWT_CUDA_OK(cudaGetLastError());
+    return GCWT_OK;
+}
+
+int generic_execute(gcwt_plan* p, const std::vector<int>& ids, const void* x, int in_type,
+                    int64_t n_channels, int64_t n_samples, int64_t x_stride, int64_t halo_l,
+                    int64_t halo_r, const double* d_means, void* out, int64_t s_stride,
+                    int64_t c_stride, cudaStream_t st) {
+    if (ids.empty()) return GCWT_OK;
+    if (p->compute_type == GCWT_F64) {
+        if (in_type == GCWT_F32)
+            return generic_run<float, double>(p, ids, (const float*)x, n_channels, n_samples, x_stride, halo_l,
+                                              halo_r, d_means, out, s_stride, c_stride, st);
+        return generic_run<double, double>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
+                                           halo_r, d_means, out, s_stride, c_stride, st);
+    }
+    if (in_type == GCWT_F32)
+        return generic_run<float, float>(p, ids, (const float*)x, n_channels, n_samples, x_stride, halo_l,
+                                         halo_r, d_means, out, s_stride, c_stride, st);
+    return generic_run<double, float>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
+                                      halo_r, d_means, out, s_stride, c_stride, st);
+}
+
+// ----------------------------------------------------------------------------- probe
+__global__ void filter_response_kernel(int64_t L, int k_first, int n_terms, const double* __restrict__ terms,
+                                       int64_t nfft, int64_t first_bin, int64_t n_bins,
+                                       double2* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bins) return;
+    const int64_t j = first_bin + i;
+    const double g = morse_response(j, nfft, L, k_first, n_terms, terms);
+    double re = g, im = 0.0;
+    if ((L & 1) == 0) {
+        double s, c;
+        sincospi(-(double)(j % (2 * nfft)) / (double)nfft, &s, &c);
+        re = g * c;
+        im = g * s;
+    }
+    out[i] = make_double2(re, im);
+}
+
+int filter_response_device(int64_t L, int k_first, int n_terms, const double* terms_host, int64_t nfft,
+                           int64_t first_bin, int64_t n_bins, double* out_host) {
+    double* d_terms = nullptr;
+    double2* d_out = nullptr;
+    GCWT_CUDA_OK(cudaMalloc((void**)&d_terms, sizeof(double) * n_terms));
+    GCWT_CUDA_OK(cudaMalloc((void**)&d_out, sizeof(double2) * n_bins));
+    GCWT_CUDA_OK(cudaMemcpy(d_terms, terms_host, sizeof(double) * n_terms, cudaMemcpyHostToDevice));
+    filter_response_kernel<<<(unsigned)((n_bins + 255) / 256), 256>>>(L, k_first, n_terms, d_terms, nfft,
+                                                                       first_bin, n_bins, d_out);
+    count_launch();
+    GCWT_CUDA_OK(cudaGetLastError());
+    GCWT_CUDA_OK(cudaMemcpy(out_host, d_out, sizeof(double2) * n_bins, cudaMemcpyDeviceToHost));
+    cudaFree(d_terms);
+    cudaFree(d_out);
+    return GCWT_OK;
+}
+
+// psi_L[n] = (1/L) sum_k X[k] e^{2 pi i k (n + (L+1)/2) / L}; phase kept as an exact
+// integer: 2 k (n + (L+1)/2) / L = k (2n + L + 1) / L half-turns.
+__global__ void morse_kernel_kernel(int64_t L, int k_first, int n_terms, const double* __restrict__ terms,
+                                    double2* __restrict__ out) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= L) return;
+    double re = 0.0, im = 0.0;
+    for (int t = 0; t < n_terms; ++t) {
+        const int64_t k = k_first + t;
+        const int64_t num = (k * ((2 * n + L + 1) % (2 * L))) % (2 * L);
+        double s, c;
+        sincospi((double)num / (double)L, &s, &c);
+        re += terms[t] * c;
+        im += terms[t] * s;
+    }
+    out[n] = make_double2(re / (double)L, im / (double)L);
+}
+
+int morse_kernel_device(int64_t L, int k_first, int n_terms, const double* terms_host, double* out_host) {
+    double* d_terms = nullptr;
+    double2* d_out = nullptr;
+    GCWT_CUDA_OK(cudaMalloc((void**)&d_terms, sizeof(double) * n_terms));
+    GCWT_CUDA_OK(cudaMalloc((void**)&d_out, sizeof(double2) * L));
+    GCWT_CUDA_OK(cudaMemcpy(d_terms, terms_host, sizeof(double) * n_terms, cudaMemcpyHostToDevice));
+    morse_kernel_kernel<<<(unsigned)((L + 255) / 256), 256>>>(L, k_first, n_terms, d_terms, d_out);
+    count_launch();
+    GCWT_CUDA_OK(cudaGetLastError());
+    GCWT_CUDA_OK(cudaMemcpy(out_host, d_out, sizeof(double2) * L, cudaMemcpyDeviceToHost));
+    cudaFree(d_terms);
+    cudaFree(d_out);
+    return GCWT_OK;
+}
+
+}  // namespace gcwt

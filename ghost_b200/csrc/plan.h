@@ -1,0 +1,92 @@
+// Internal plan representation shared by the path drivers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include "../../include/ghost_cwt.h"
+
+namespace gcwt {
+
+constexpr int kBins = 256;          // spectrum bins kept per chunk by the band-limited path
+constexpr int kChunkDec = 1024;     // chunk length in decimated samples (forward FFT size)
+constexpr int kFullN = 4096;        // chunk length of the full-spectrum fused kernel
+constexpr int kMaxClassScales = 16; // scales handled by one fused launch (shared-memory table)
+constexpr int kMinFastLevel = 2;    // P = kChunkDec * 2^level / kBins must be >= 16
+constexpr int kHalfbandT = 19;      // half-band taps run from -T..T
+constexpr int kHalfbandOdd = (kHalfbandT + 1) / 2;
+
+struct ScaleInfo {                  // mirrored on the device (generic path)
+    int64_t L;
+    int32_t k_first;
+    int32_t n_terms;
+    int32_t term_off;
+    int32_t level;                  // >=0 fast level, -1 full fused, -2 generic
+};
+
+struct FastClass {
+    int level = 0;                  // -1: full-spectrum kernel at full rate
+    int64_t nc_full = 0;            // chunk length in full-rate samples
+    int64_t lmax = 0;
+    int64_t offset = 0;             // first owned chunk-local sample
+    int64_t hop = 0;                // owned samples per chunk
+    std::vector<int> scale_ids;     // global scale indices, <= kMaxClassScales
+    // banded: float2 [n][kBins] (response / decimator, incl. 1/kChunkDec)
+    // full:   float2 [n][kFullN] (response incl. 1/kFullN)
+    float2* d_table = nullptr;
+    int32_t* d_scale_ids = nullptr;
+};
+
+struct Workspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace gcwt
+
+struct gcwt_plan {
+    int n_scales = 0;
+    int compute_type = GCWT_F32;
+    int out_kind = GCWT_OUT_AMPLITUDE;
+    int device = 0;
+    int flags = 0;
+    double band_tol = 3e-7;
+    std::vector<gcwt::ScaleInfo> scales;
+    std::vector<double> terms;
+    gcwt::ScaleInfo* d_scales = nullptr;
+    double* d_terms = nullptr;
+    std::vector<gcwt::FastClass> classes;   // fp32 fused-kernel groups
+    std::vector<int> generic_ids;           // scales served by the generic path
+    int max_level = 0;
+    double halfband_odd[gcwt::kHalfbandOdd];  // h[1], h[3], ... (h[0] = 0.5)
+    gcwt::Workspace ws;
+    bool profile = false;
+    struct Span { cudaEvent_t a, b; int kind; int launches; };
+    std::vector<Span> spans;
+    double prof_ms[GCWT_PROFILE_KINDS] = {0, 0, 0, 0};
+    int64_t prof_launches[GCWT_PROFILE_KINDS] = {0, 0, 0, 0};
+    double* d_means = nullptr;              // internal per-channel means
+    int64_t means_cap = 0;
+};
+
+namespace gcwt {
+int ensure_workspace(gcwt_plan* p, size_t bytes);
+void count_launch(int n = 1);
+int64_t launches_so_far();
+// RAII-less profiling span: begin returns an index (or -1 when profiling is off)
+int prof_begin(gcwt_plan* p, int kind, cudaStream_t st);
+void prof_end(gcwt_plan* p, int idx, cudaStream_t st);
+
+// path drivers (each returns a GCWT_* code)
+int generic_execute(gcwt_plan* p, const std::vector<int>& ids, const void* x, int in_type,
+                    int64_t n_channels, int64_t n_samples, int64_t x_stride,
+                    int64_t halo_l, int64_t halo_r, const double* d_means,
+                    void* out, int64_t s_stride, int64_t c_stride, cudaStream_t st);
+int fast_execute(gcwt_plan* p, const void* x, int in_type,
+                 int64_t n_channels, int64_t n_samples, int64_t x_stride,
+                 int64_t halo_l, int64_t halo_r, const double* d_means,
+                 void* out, int64_t s_stride, int64_t c_stride, cudaStream_t st);
+int fast_plan_build(gcwt_plan* p);       // classify scales + upload tables (fp32 plans)
+void fast_plan_free(gcwt_plan* p);
+int means_launch(const void* x, int in_type, int64_t n_channels, int64_t n_samples,
+                 int64_t x_stride, double* d_means, cudaStream_t st);
+}  // namespace gcwt

@@ -1,0 +1,188 @@
+"""Thin Python handle on a device plan (ctypes over include/ghost_cwt.h).
+
+PyTorch supplies device buffers and streams only; all arithmetic happens in
+libghostcwt.so.  A plan is built from the host planner's per-scale tables and is
+independent of the recording length.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["CwtPlan", "scale_tables", "OUT_KINDS"]
+
+OUT_KINDS = {"complex": _lib.OUT_COMPLEX, "amplitude": _lib.OUT_AMPLITUDE, "power": _lib.OUT_POWER}
+
+
+def scale_tables(wavelet, norm_radian_freqs, lengths):
+    """Per-scale (k_first, n_terms, concatenated X[k]) for the C plan descriptor."""
+    k_first, n_terms, terms = [], [], []
+    for w, L in zip(np.atleast_1d(norm_radian_freqs), np.atleast_1d(lengths)):
+        k0, X = wavelet.spectrum_terms(int(L), float(w))
+        k_first.append(k0)
+        n_terms.append(len(X))
+        terms.append(X)
+    return (np.asarray(k_first, dtype=np.int32), np.asarray(n_terms, dtype=np.int32),
+            np.ascontiguousarray(np.concatenate(terms), dtype=np.float64))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class CwtPlan:
+    """Device tables for one set of scales."""
+
+    def __init__(self, lengths, k_first, n_terms, terms, *, dtype=np.float32, output="amplitude",
+                 device=0, force_generic=False, band_tol=0.0):
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("dtype must be float32 or float64 but got {}".format(dtype))
+        if output not in OUT_KINDS:
+            raise ValueError("output must be 'amplitude', 'power' or 'complex' but got {}".format(output))
+        self.lib = _lib.load()
+        self.dtype = dtype
+        self.output = output
+        self.device = int(device)
+        self.lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        self.n_scales = int(self.lengths.size)
+        self._k_first = np.ascontiguousarray(k_first, dtype=np.int32)
+        self._n_terms = np.ascontiguousarray(n_terms, dtype=np.int32)
+        self._terms = np.ascontiguousarray(terms, dtype=np.float64)
+        desc = _lib.PlanDesc()
+        desc.n_scales = self.n_scales
+        desc.lengths = self.lengths.ctypes.data_as(C.POINTER(C.c_int64))
+        desc.k_first = self._k_first.ctypes.data_as(C.POINTER(C.c_int32))
+        desc.n_terms = self._n_terms.ctypes.data_as(C.POINTER(C.c_int32))
+        desc.terms = self._terms.ctypes.data_as(C.POINTER(C.c_double))
+        desc.compute_type = _lib.F32 if dtype == np.float32 else _lib.F64
+        desc.out_kind = OUT_KINDS[output]
+        desc.device = self.device
+        desc.flags = _lib.FLAG_FORCE_GENERIC if force_generic else 0
+        desc.band_tol = float(band_tol)
+        handle = C.c_void_p()
+        _lib.check(self.lib.gcwt_plan_create(C.byref(handle), C.byref(desc)))
+        self._h = handle
+
+    # ------------------------------------------------------------------ info
+    @property
+    def max_length(self):
+        return int(self.lengths.max())
+
+    def levels(self):
+        out = np.empty(self.n_scales, dtype=np.int32)
+        _lib.check(self.lib.gcwt_plan_levels(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def workspace_bytes(self):
+        return int(self.lib.gcwt_plan_workspace_bytes(self._h))
+
+    @property
+    def torch_out_dtype(self):
+        torch = _torch()
+        if self.output == "complex":
+            return torch.complex64 if self.dtype == np.float32 else torch.complex128
+        return torch.float32 if self.dtype == np.float32 else torch.float64
+
+    # ------------------------------------------------------------------ run
+    def alloc_out(self, n_channels, n_samples):
+        torch = _torch()
+        return torch.empty((n_channels, self.n_scales, n_samples), dtype=self.torch_out_dtype,
+                           device="cuda:%d" % self.device)
+
+    def channel_means(self, x, n_samples=None):
+        """float64 mean per channel of a (C, N) device tensor (reference transforms.py:143)."""
+        torch = _torch()
+        n = x.shape[1] if n_samples is None else int(n_samples)
+        means = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
+        in_type = _lib.F32 if x.dtype == torch.float32 else _lib.F64
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self.lib.gcwt_channel_means(x.data_ptr(), in_type, x.shape[0], n, x.stride(0),
+                                               means.data_ptr(), self.device, st))
+        return means
+
+    def execute(self, x, out=None, *, means=None, start=0, stop=None, halo_left=0, halo_right=0):
+        """Transform samples ``[start, stop)`` of every channel of ``x`` (C, N) into
+        ``out[:, :, start:stop]`` (C, S, N).  ``x`` and ``out`` are CUDA tensors."""
+        torch = _torch()
+        if x.dim() != 2 or not x.is_cuda or x.stride(1) != 1:
+            raise ValueError("x must be a (channels, samples) CUDA tensor with unit sample stride")
+        if x.dtype not in (torch.float32, torch.float64):
+            raise ValueError("x must be float32 or float64")
+        n_ch, n_all = x.shape
+        stop = n_all if stop is None else int(stop)
+        start = int(start)
+        if not (0 <= start < stop <= n_all):
+            raise ValueError("bad segment [{}, {})".format(start, stop))
+        if halo_left > start or halo_right > n_all - stop:
+            raise ValueError("halo reaches outside the tensor")
+        if out is None:
+            out = self.alloc_out(n_ch, n_all)
+        if out.dtype != self.torch_out_dtype or out.dim() != 3 or out.stride(2) != 1 \
+                or out.shape[0] != n_ch or out.shape[1] != self.n_scales or out.shape[2] != n_all:
+            raise ValueError("out must be (channels, scales, samples) of dtype %s" % self.torch_out_dtype)
+        esz = x.element_size()
+        osz = out.element_size()
+        mptr = None
+        if means is not None:
+            if means.dtype != torch.float64 or means.numel() != n_ch or not means.is_cuda:
+                raise ValueError("means must be a float64 CUDA tensor with one entry per channel")
+            mptr = means.data_ptr()
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        in_type = _lib.F32 if x.dtype == torch.float32 else _lib.F64
+        _lib.check(self.lib.gcwt_execute(
+            self._h, x.data_ptr() + start * esz, in_type, n_ch, stop - start, x.stride(0),
+            int(halo_left), int(halo_right), mptr,
+            out.data_ptr() + start * osz, out.stride(1), out.stride(0), st))
+        return out
+
+    def execute_host(self, x, out=None, means=None):
+        """Host-buffer entry point (numpy in, numpy out) through gcwt_execute_host."""
+        x = np.ascontiguousarray(x)
+        if x.ndim == 1:
+            x = x[None, :]
+        if x.dtype not in (np.float32, np.float64):
+            x = x.astype(np.float64)
+        n_ch, n = x.shape
+        if self.output == "complex":
+            odt = np.complex64 if self.dtype == np.float32 else np.complex128
+        else:
+            odt = self.dtype
+        if out is None:
+            out = np.empty((n_ch, self.n_scales, n), dtype=odt)
+        assert out.dtype == odt and out.flags.c_contiguous and out.shape == (n_ch, self.n_scales, n)
+        mptr = None
+        if means is not None:
+            means = np.ascontiguousarray(means, dtype=np.float64)
+            mptr = means.ctypes.data
+        in_type = _lib.F32 if x.dtype == np.float32 else _lib.F64
+        _lib.check(self.lib.gcwt_execute_host(self._h, x.ctypes.data, in_type, n_ch, n, x.strides[0] // x.itemsize,
+                                              mptr, out.ctypes.data, n, n * self.n_scales))
+        return out
+
+    PROFILE_KINDS = ("mean+pyramid", "fused_full", "fused_banded", "generic")
+
+    def profile(self, on=True):
+        _lib.check(self.lib.gcwt_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        """{family: (milliseconds, launches)} accumulated since the last reset."""
+        ms = (C.c_double * 4)()
+        ln = (C.c_int64 * 4)()
+        _lib.check(self.lib.gcwt_profile_read(self._h, ms, ln, 1 if reset else 0))
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(self.PROFILE_KINDS)}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.gcwt_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

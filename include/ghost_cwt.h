@@ -1,0 +1,154 @@
+/* ghost_cwt.h -- C ABI of the B200-native Morse-wavelet CWT hot path.
+ *
+ * The reference (nelpy/ghost) has no FFI: its boundary for this path is the Python
+ * class ghost.wave.ContinuousWaveletTransform.  Inside transform() there are exactly
+ * two seams, and this ABI replaces what sits behind them:
+ *
+ *   kernel, _ = wv(length)                       ghost/wave/transforms.py:197
+ *       -> Morse.__call__                        ghost/wave/morse.py:53-91
+ *       -> morsewave / _morsewave                ghost/wave/morseutils.py:22-151
+ *   res = convfun(x[start:stop], kernel)         ghost/wave/transforms.py:203
+ *       -> fastconv_scipy / fastconv_fftw        ghost/sigtools/convolution.py:16-216
+ *   out_array[idx, start:stop] = np.abs(res)     ghost/wave/transforms.py:204
+ *
+ * plus the mean removal (transforms.py:142-143).  The frequency grid and the per-scale
+ * tap counts L stay on the host in float64 with the reference's operation order
+ * (transforms.py:147-182, morse.py:93-122) because they must be bit-identical; they are
+ * passed in through gcwt_plan_desc together with the non-zero samples X[k] of each
+ * scale's L-point Morse spectrum (morseutils.py:129-133,178).
+ *
+ * All functions return 0 on success or a negative GCWT_ERR_* code; the message for the
+ * last failure on the calling thread is available from gcwt_last_error().  There is no
+ * CPU fallback: every entry point that computes needs a CUDA device.
+ */
+#ifndef GHOST_CWT_H
+#define GHOST_CWT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCWT_VERSION 100
+
+/* error codes */
+#define GCWT_OK            0
+#define GCWT_ERR_ARG      -1
+#define GCWT_ERR_CUDA     -2
+#define GCWT_ERR_NOMEM    -3
+#define GCWT_ERR_UNSUPPORTED -4
+
+/* element types */
+#define GCWT_F32 0
+#define GCWT_F64 1
+
+/* what the epilogue writes (kernel (3) of the design): the reference stores |W|
+ * (transforms.py:204); power is amplitude**2 (transforms.py:507-510); complex is the
+ * value before np.abs. */
+#define GCWT_OUT_COMPLEX   0
+#define GCWT_OUT_AMPLITUDE 1
+#define GCWT_OUT_POWER     2
+
+/* plan flags */
+#define GCWT_FLAG_FORCE_GENERIC 1   /* fp32 only: skip the band-limited fast path */
+
+typedef struct gcwt_plan gcwt_plan;
+
+typedef struct gcwt_plan_desc {
+    int32_t        n_scales;
+    const int64_t *lengths;      /* [n_scales] tap count L per scale (morse.py:108-122)          */
+    const int32_t *k_first;      /* [n_scales] first L-grid bin with a non-zero spectrum sample   */
+    const int32_t *n_terms;      /* [n_scales] number of consecutive non-zero samples             */
+    const double  *terms;        /* concatenated X[k] values, sum(n_terms) doubles                */
+    int32_t        compute_type; /* GCWT_F32 or GCWT_F64: arithmetic and output element type      */
+    int32_t        out_kind;     /* GCWT_OUT_*                                                    */
+    int32_t        device;       /* CUDA device ordinal                                           */
+    int32_t        flags;        /* GCWT_FLAG_*                                                   */
+    double         band_tol;     /* fp32 fast path: allowed out-of-band filter energy (amplitude
+                                    ratio); 0 selects the default 3e-7                            */
+} gcwt_plan_desc;
+
+/* Build device tables for a set of scales.  Replaces the per-scale kernel synthesis
+ * Morse.__call__ (morse.py:53-91). */
+int gcwt_plan_create(gcwt_plan **out, const gcwt_plan_desc *desc);
+int gcwt_plan_destroy(gcwt_plan *plan);
+
+/* Introspection: per scale, the decimation level the planner chose (>= 0: band-limited
+ * fast path at 2**level; -1: full-spectrum fused kernel; -2: generic global-memory path). */
+int gcwt_plan_levels(const gcwt_plan *plan, int32_t *levels_out);
+
+/* Transform one contiguous segment (an epoch, or one rank's time shard) of n_channels
+ * channels.  Replaces, for every scale, convfun(x[start:stop], kernel) followed by
+ * np.abs (transforms.py:202-204), i.e. a zero-padded 'same' linear convolution.
+ *
+ *   x            device pointer to sample 0 of channel 0 of the segment; element type in_type
+ *   x_stride     elements between channels
+ *   halo_left / halo_right
+ *                number of REAL samples readable before x[0] / after x[n_samples-1] in each
+ *                channel (0 at true signal or epoch edges, where the reference zero-pads;
+ *                > 0 for time shards so that shard seams carry no edge effect)
+ *   means        device pointer to one double per channel that is subtracted from every
+ *                sample (the reference removes the GLOBAL mean, transforms.py:143), or NULL
+ *                to use the mean of the segment itself
+ *   out          device pointer; coefficient (c, s, n) is written at
+ *                out[c * out_channel_stride + s * out_scale_stride + n] in units of the
+ *                output element (float/double, or float2/double2 for GCWT_OUT_COMPLEX)
+ *   stream       cudaStream_t (may be NULL for the default stream)
+ */
+int gcwt_execute(gcwt_plan *plan, const void *x, int32_t in_type,
+                 int64_t n_channels, int64_t n_samples, int64_t x_stride,
+                 int64_t halo_left, int64_t halo_right, const double *means,
+                 void *out, int64_t out_scale_stride, int64_t out_channel_stride,
+                 void *stream);
+
+/* Same, with HOST pointers (no halos): allocates device buffers, copies in, runs,
+ * copies out, synchronises.  The call a ctypes/cgo-style binding makes when the caller
+ * has no device memory of its own. */
+int gcwt_execute_host(gcwt_plan *plan, const void *x, int32_t in_type,
+                      int64_t n_channels, int64_t n_samples, int64_t x_stride,
+                      const double *means_host,
+                      void *out, int64_t out_scale_stride, int64_t out_channel_stride);
+
+/* Per-channel mean in float64 (transforms.py:143): means[c] = mean(x[c, 0:n_samples]). */
+int gcwt_channel_means(const void *x, int32_t in_type, int64_t n_channels,
+                       int64_t n_samples, int64_t x_stride, double *means_dev,
+                       int32_t device, void *stream);
+
+/* Exact transfer function of one scale's reference kernel on an n_fft-point DFT grid
+ * (device evaluation of the closed form; used by tests and by INTEGRATION examples).
+ * Writes n_bins complex doubles (re, im interleaved) for bins first_bin.. to host memory. */
+int gcwt_filter_response(int64_t length, int32_t k_first, int32_t n_terms,
+                         const double *terms, int64_t n_fft, int64_t first_bin,
+                         int64_t n_bins, double *out_host, int32_t device);
+
+/* The L-tap time-domain kernel psi_L itself (what Morse.__call__ returns first,
+ * ghost/wave/morse.py:84-91 -> morseutils.py:145-149), synthesised on the device as the
+ * sum of its n_terms complex exponentials.  Writes `length` complex doubles to host. */
+int gcwt_morse_kernel(int64_t length, int32_t k_first, int32_t n_terms, const double *terms,
+                      double *out_host, int32_t device);
+
+/* Bytes of device workspace the plan currently holds (grows on demand in execute). */
+size_t gcwt_plan_workspace_bytes(const gcwt_plan *plan);
+
+/* Per-kernel-family device timing for the roofline report.  With profiling enabled,
+ * gcwt_execute brackets every launch group with CUDA events on the launch stream.
+ * gcwt_profile_read synchronises those events and returns accumulated milliseconds and
+ * launch counts for: [0] mean + decimation pyramid, [1] fused full-spectrum kernel,
+ * [2] fused band-limited kernel, [3] generic global-memory path. */
+#define GCWT_PROFILE_KINDS 4
+int gcwt_profile_enable(gcwt_plan *plan, int32_t on);
+int gcwt_profile_read(gcwt_plan *plan, double *ms_out, int64_t *launches_out, int32_t reset);
+
+/* Number of kernel launches issued by this library on the calling thread since the
+ * last call with reset != 0 (bench.py reports it as gpu_launches). */
+int64_t gcwt_launch_count(int32_t reset);
+
+const char *gcwt_last_error(void);
+int gcwt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GHOST_CWT_H */
