@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the Morse-wavelet CWT hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo, N ranks via torchrun
+    python bench.py --impl reference --steps K --warmup W    # CPU oracle port on the host cores
+
+A step is one pass of the transform over one batch of synthetic chirp + pink-noise
+channels.  Workload at N = 1 is config 2 of BASELINE.json (64 channels x 1.25 kHz x
+30 min, 96 scales, fp32 amplitude); at N > 1 the channels are sharded over the ranks with
+the same 64 channels per GPU (weak scaling, no data-path collective).
+
+One JSON line is printed by rank 0 (see the driver contract in the task statement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cwt_output_coeffs_per_sec"
+UNIT = "coeff/s"
+
+WORKLOADS = {
+    # name: fs, samples, channels per GPU, freq_limits, voices/octave, output
+    "cfg2": dict(fs=1250.0, n=2250000, channels=64, freq_limits=[0.40, 300.0], vpo=10, output="amplitude",
+                 desc="64ch x 1.25kHz x 30min, 96 scales, fp32 amplitude"),
+    "cfg1": dict(fs=1000.0, n=60000, channels=1, freq_limits=None, vpo=10, output="amplitude",
+                 desc="1ch x 1kHz x 60s, 84 scales, fp32 amplitude"),
+    "cfg3slice": dict(fs=30000.0, n=18000000, channels=2, freq_limits=[1.7, 15000.0], vpo=10, output="power",
+                      desc="2ch of cfg3 (30kHz x 10min, 128 scales, fp32 power)"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--channels", type=int, default=None, help="channels per GPU (default: workload's)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    return ap.parse_args()
+
+
+def plan_frequencies(wl):
+    from ghost_b200 import ContinuousWaveletTransform
+    cwt = ContinuousWaveletTransform(dtype=np.float32)
+    cwt.fs = wl["fs"]
+    cwt.wavelet.fs = wl["fs"]
+    return np.asarray(cwt.plan_frequencies(wl["n"], freq_limits=wl["freq_limits"], voices_per_octave=wl["vpo"]))
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region, through in-process NVML
+    (an nvidia-smi subprocess per sample stalls the driver for hundreds of ms)."""
+
+    def __init__(self, index=0, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz, self.power = None, []
+        self.nv = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        nv = self.nv
+        if nv is None:
+            return
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+                if get_reasons is not None:
+                    r = int(get_reasons(self.handle))
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+               "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+               "source": "nvml" if self.nv is not None else "unavailable"}
+        if self.power:
+            out["power_w_max"] = float(max(self.power))
+        return out
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_sample(wl, freqs, seconds_hint):
+    """Time the oracle port (reference algorithm, scipy FFT, ThreadPool over scales) on a
+    bounded sample: one channel, a prefix of the recording, all scales."""
+    from multiprocessing import cpu_count
+    from ghost_b200 import synth
+    from oracle import cwt_oracle as orc
+    n = wl["n"]
+    # the reference needs roughly 0.3 us per coefficient per core; bound the sample
+    est_full = 3.0e-7 * n * len(freqs) / max(1, min(cpu_count(), len(freqs)))
+    n_s = n if est_full <= seconds_hint else max(int(n * seconds_hint / est_full), int(5 * 1.2 * 45000))
+    n_s = min(n, n_s)
+    x = synth.chirp_pink(n_s, wl["fs"], 0, np.float32)
+    t0 = time.perf_counter()
+    orc.cwt_amplitude(x, wl["fs"], frequencies=freqs, parallel=True)
+    dt = time.perf_counter() - t0
+    coeffs = n_s * len(freqs)
+    return coeffs / dt, dt, n_s, cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = dict(WORKLOADS[args.workload])
+    freqs = plan_frequencies(wl)
+    from multiprocessing import cpu_count
+    from ghost_b200 import synth
+    from oracle import cwt_oracle as orc
+    # per step: one channel x a bounded prefix x all scales, all host threads
+    rate, dt, n_s, cores = cpu_sample(wl, freqs, 8.0)
+    x = synth.chirp_pink(n_s, wl["fs"], 0, np.float32)
+    for _ in range(max(0, args.warmup - 1)):
+        orc.cwt_amplitude(x, wl["fs"], frequencies=freqs, parallel=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.cwt_amplitude(x, wl["fs"], frequencies=freqs, parallel=True)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n_s * len(freqs) / dt
+    sample = "1 channel x %d samples x %d scales per step (oracle port of the reference, parallel=True)" % (
+        n_s, len(freqs))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + wl["desc"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ghost_b200 import Morse, synth, _lib
+    from ghost_b200.engine import CwtPlan, scale_tables
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    wl = dict(WORKLOADS[args.workload])
+    if args.channels:
+        wl["channels"] = args.channels
+    fs, n, nch = wl["fs"], wl["n"], wl["channels"]
+    freqs = plan_frequencies(wl)
+    m = Morse(fs=fs)
+    om = freqs / (fs / 2.0) * np.pi
+    L = m.compute_lengths(om)
+    k0, nt, terms = scale_tables(m, om, L)
+    plan = CwtPlan(L, k0, nt, terms, dtype=np.float32, output=wl["output"], device=local)
+    S = len(freqs)
+
+    # synthetic channels of this rank (channel shard: rank r owns channels r*nch .. r*nch+nch-1);
+    # distinct seeds for the first 8, then reuse (generation cost only)
+    base = [synth.chirp_pink(n, fs, rank * nch + c, np.float32) for c in range(min(nch, 8))]
+    x_host = torch.empty((nch, n), dtype=torch.float32).pin_memory()
+    for c in range(nch):
+        x_host[c] = torch.from_numpy(base[c % len(base)])
+        if c >= len(base):
+            x_host[c] = torch.roll(x_host[c], 1009 * c)
+    x_dev = x_host.to(dev, non_blocking=True)
+    out = plan.alloc_out(nch, n)
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing --------------------------------------------------
+    for _ in range(args.warmup):
+        plan.execute(x_dev, out)
+    barrier()
+    plan.profile(True)
+    plan.profile_read(reset=True)
+    _lib.launch_count(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        plan.execute(x_dev, out)
+    ev1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count()
+    prof = plan.profile_read(reset=True)
+    plan.profile(False)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    coeffs_rank = float(nch) * n * S
+    value = coeffs_rank * world / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused band-limited kernel) ------------------
+    levels = plan.levels()
+    out_el = 8 if wl["output"] == "complex" else 4
+    n_banded = int((levels >= 0).sum())
+    n_full = int((levels == -1).sum())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    ms_banded, ln_banded = prof["fused_banded"]
+    n_class_launches = max(1, ln_banded)
+    # algorithmic bytes of all banded launches of one step: its output rows, plus one read of the input
+    bytes_banded_step = float(nch) * n * (n_banded * out_el + 4)
+    ach = bytes_banded_step * args.steps / (ms_banded * 1e-3) / 1e9 if ms_banded > 0 else None
+    roof = {"bound": "hbm", "kernel": "fused_banded_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+            "launches": ln_banded, "ms_per_step": ms_banded / args.steps,
+            "share_of_step": ms_banded / ms_total if ms_total > 0 else None,
+            "bytes_per_step": bytes_banded_step,
+            "other_kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if k != "fused_banded"},
+            "whole_step": {"achieved": float(nch) * n * (S * out_el + 4) / (ms_step * 1e-3) / 1e9,
+                           "frac": float(nch) * n * (S * out_el + 4) / (ms_step * 1e-3) / 1e9 / peak}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roof["traffic"] = json.load(open(traffic_file)).get("fused_banded_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the host-buffer path ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, plan, x_host, dev, world, nch, n, S, out_el)
+
+    # ---- CPU baseline (rank 0, N = 1) ------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, dt, n_s, cores = cpu_sample(wl, freqs, args.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+               "sample": "1 channel x %d samples x %d scales (oracle port of the reference: scipy FFT overlap-add, "
+                         "ThreadPool over scales)" % (n_s, S)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "channels_per_gpu": nch, "samples": n,
+                       "scales": S, "fs": fs, "output": wl["output"], "parallelism": "channel-shard x%d" % world,
+                       "l2_policy": "inputs (%.2f GB) and outputs (%.1f GB) per step exceed the 126 MB L2" % (
+                           nch * n * 4 / 1e9, coeffs_rank * out_el / 1e9),
+                       "scale_classes": {"band_limited": n_banded, "full_spectrum": n_full,
+                                         "generic": int((levels == -2).sum())}},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, plan, x_host, dev, world, nch, n, S, out_el):
+    """Host buffers in, host buffers out: per step every channel group is copied H2D from
+    pinned memory, transformed, and its coefficients copied D2H into a pinned ring."""
+    import torch
+    import torch.distributed as dist
+    group = max(1, min(nch, int(2.0e9 // (n * S * out_el)) or 1))
+    ring = [torch.empty((group, S, n), dtype=plan.torch_out_dtype).pin_memory() for _ in range(2)]
+    dbuf = [plan.alloc_out(group, n) for _ in range(2)]
+    xin = [torch.empty((group, n), dtype=torch.float32, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    done = [torch.cuda.Event() for _ in range(2)]
+    computed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
+
+    def one_step():
+        i = 0
+        for c0 in range(0, nch, group):
+            g = min(group, nch - c0)
+            b = i & 1
+            main.wait_event(done[b])                       # ring slot free again
+            xin[b][:g].copy_(x_host[c0:c0 + g], non_blocking=True)
+            plan.execute(xin[b][:g], dbuf[b][:g])
+            computed[b].record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(computed[b])
+                ring[b][:g].copy_(dbuf[b][:g], non_blocking=True)
+                done[b].record(copy_stream)
+            i += 1
+        copy_stream.synchronize()
+
+    steps = max(1, min(args.steps, 3))
+    one_step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    torch.cuda.synchronize(dev)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sec = float(dt.item()) / steps
+    checksum = float(ring[0][0, 0, :1000].double().sum())
+    return {"value": float(nch) * n * S * world / sec, "unit": UNIT, "h2d_bytes_per_step": int(nch * n * 4),
+            "d2h_bytes_per_step": int(nch * n * S * out_el), "ms_per_step": sec * 1e3, "steps": steps,
+            "channel_group": group, "api": "CwtPlan.execute on pinned host buffers, D2H of all coefficients",
+            "checksum": checksum}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

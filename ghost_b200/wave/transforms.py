@@ -187,9 +187,17 @@ class ContinuousWaveletTransform(WaveletTransform):
         frequencies = np.asarray(self.plan_frequencies(int(np.min(lengths)), freq_limits=freq_limits,
                                                        freqs=freqs, voices_per_octave=voices_per_octave),
                                  dtype=np.float64)
-        if frequencies.size == 0:
-            raise ValueError("no analysis frequency lies inside the usable range")
         self._frequencies = frequencies
+        if frequencies.size == 0:
+            # data too short for any scale: the reference ends up with a (0, N) array
+            self._multichannel = bool(multichannel)
+            self._result = None
+            cdt = np.dtype(self._dtype)
+            if self._output == "complex":
+                cdt = np.dtype(np.complex64 if self._dtype == np.float32 else np.complex128)
+            shape = (x_host.shape[0], 0, x_host.shape[1]) if multichannel else (0, x_host.shape[1])
+            self._host = np.zeros(shape, dtype=cdt)
+            return
         plan = self._get_plan(frequencies)
 
         dev = torch.device("cuda", self._device)
