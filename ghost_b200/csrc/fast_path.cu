@@ -213,6 +213,7 @@ struct FusedParams {
     const double* means;      // full only
     int log2d;                // banded: log2 of the decimation factor
     int p_cols;               // banded: P = nc_full / kBins (columns per chunk)
+    int log2p;                // log2(P)
     float inv_nc;             // 1 / nc_full
     int64_t offset, hop, n_chunks, n;
     int n_scales;
@@ -224,11 +225,46 @@ struct FusedParams {
     int units_per_chunk;
 };
 
+__device__ __forceinline__ float sqrt_approx(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));       // one MUFU op, rel. error 2^-23
+    return r;
+}
+
+template <int KIND> struct out_elem { typedef float type; };
+template <> struct out_elem<GCWT_OUT_COMPLEX> { typedef float2 type; };
+
+// Epilogue (kernel (3)): complex, |W| or |W|^2 of 16 register-resident outputs that lie
+// `stride` elements apart; bit k of `mask` says whether output k is owned by this chunk.
+__device__ __forceinline__ void st_pred(float* p, float v, unsigned on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}"
+                 :: "l"(p), "f"(v), "r"(on) : "memory");
+}
+__device__ __forceinline__ void st_pred(float2* p, float2 v, unsigned on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.v2.f32 [%0], {%1, %2};\n\t}"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "r"(on) : "memory");
+}
+
 template <int KIND>
-__device__ __forceinline__ void store_coeff(void* out, int64_t idx, float2 v) {
-    if (KIND == GCWT_OUT_COMPLEX) ((float2*)out)[idx] = v;
-    else if (KIND == GCWT_OUT_AMPLITUDE) ((float*)out)[idx] = sqrtf(v.x * v.x + v.y * v.y);
-    else ((float*)out)[idx] = v.x * v.x + v.y * v.y;
+__device__ __forceinline__ void store_column(typename out_elem<KIND>::type* __restrict__ op, int64_t stride,
+                                             unsigned mask, const float2* a) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const unsigned on = mask & (1u << k);                     // predicated store: no divergent branch
+        if constexpr (KIND == GCWT_OUT_COMPLEX) st_pred(op + k * stride, a[k], on);
+        else if constexpr (KIND == GCWT_OUT_AMPLITUDE) st_pred(op + k * stride, sqrt_approx(a[k].x * a[k].x + a[k].y * a[k].y), on);
+        else st_pred(op + k * stride, a[k].x * a[k].x + a[k].y * a[k].y, on);
+    }
+}
+
+// bits k in [0,16) with lo <= rel + (k << sh) < hi
+__device__ __forceinline__ unsigned valid_mask(int rel, int sh, int lo, int hi) {
+    const int step = 1 << sh;
+    int k_lo = (lo - rel + step - 1) >> sh;
+    int k_hi = (hi - rel + step - 1) >> sh;
+    k_lo = max(k_lo, 0);
+    k_hi = min(max(k_hi, 0), 16);
+    return k_hi > k_lo ? (((1u << k_hi) - 1u) & ~((1u << k_lo) - 1u)) : 0u;
 }
 
 // In-place-ish radix-4 Stockham FFT in shared memory, forward sign, N = 4^PASSES points,
@@ -316,10 +352,17 @@ fused_banded_kernel(const FusedParams prm) {
     }
     __syncthreads();
 
+    typedef typename out_elem<KIND>::type OutT;
     const int iters = min(prm.iters, prm.p_cols / 16 - unit * prm.iters);
+    const int lp = prm.log2p;
+    const int own_lo = (int)prm.offset;
+    const int own_hi = (int)min(prm.offset + prm.hop, prm.n - t0);       // chunk-local, <= nc_full
+    const int64_t kstride = (int64_t)16 << lp;
+    OutT* const out_c = (OutT*)prm.out + c * prm.c_stride + t0;
     int buf = 0;
     for (int it = 0; it < iters; ++it) {
-        const int n2 = col0 + it * 16 + r;
+        const int rel = col0 + it * 16 + r + (g << lp);                  // chunk-local sample of output k = 0
+        const unsigned mask = valid_mask(rel, lp + 4, own_lo, own_hi);
         for (int s = 0; s < prm.n_scales; ++s) {
             float2 a[16];
             const float2* z = Zs + s * kBins + g;
@@ -327,21 +370,15 @@ fused_banded_kernel(const FusedParams prm) {
             for (int i = 0; i < 16; ++i) a[i] = cmul(z[16 * i], R[i]);
             dft16<+1>(a);
             float2* e = ex + buf * 4096 + (g * 16) * 16 + r;
+            e[0] = a[0];                                                  // tw[0] == 1
 #pragma unroll
-            for (int k = 0; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
+            for (int k = 1; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
             __syncthreads();
             const float2* e2 = ex + buf * 4096 + g * 16 + r;
 #pragma unroll
             for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
             dft16<+1>(a);
-            // ---- (3) epilogue ---------------------------------------------------
-            const int64_t obase = c * prm.c_stride + (int64_t)prm.scale_ids[s] * prm.s_stride;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int64_t i = (int64_t)(g + 16 * k) * prm.p_cols + n2;   // chunk-local sample
-                const int64_t t = t0 + i;
-                if (i >= prm.offset && i < prm.offset + prm.hop && t < prm.n) store_coeff<KIND>(prm.out, obase + t, a[k]);
-            }
+            store_column<KIND>(out_c + (int64_t)prm.scale_ids[s] * prm.s_stride + rel, kstride, mask, a);
             buf ^= 1;
         }
 #pragma unroll
@@ -386,6 +423,10 @@ fused_full_kernel(const FusedParams prm) {
         tw[k] = expipi((float)(2 * g * k) * (1.0f / 256.0f));
         tw4k[k] = expipi((float)(2 * tid * k) * (1.0f / 4096.0f));
     }
+    typedef typename out_elem<KIND>::type OutT;
+    const int rel = g * 16 + r;                                          // chunk-local sample of output k = 0
+    const unsigned mask = valid_mask(rel, 8, (int)prm.offset, (int)min(prm.offset + prm.hop, prm.n - t0));
+    OutT* const out_c = (OutT*)prm.out + c * prm.c_stride + t0;
     for (int s = 0; s < prm.n_scales; ++s) {
         float2 a[16];
         // pre-pass: radix-16 over mu for spectrum bin m' = tid
@@ -394,27 +435,22 @@ fused_full_kernel(const FusedParams prm) {
         for (int k = 0; k < 16; ++k) a[k] = cmul(Yf[tid + 256 * k], tab[256 * k]);
         dft16<+1>(a);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) A[tid * 16 + (k ^ (tid & 15))] = cmul(a[k], tw4k[k]);
+        for (int k = 0; k < 16; ++k) A[tid * 16 + (k ^ (tid & 15))] = k ? cmul(a[k], tw4k[k]) : a[k];
         __syncthreads();
         // pass 1 of the 256-point transforms (16 columns)
 #pragma unroll
         for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 16 + (r ^ g)];
         dft16<+1>(a);
         float2* e = ex + (g * 16) * 16 + r;
+        e[0] = a[0];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
+        for (int k = 1; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
         __syncthreads();
         const float2* e2 = ex + g * 16 + r;
 #pragma unroll
         for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
         dft16<+1>(a);
-        const int64_t obase = c * prm.c_stride + (int64_t)prm.scale_ids[s] * prm.s_stride;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int64_t i = (int64_t)(g + 16 * k) * 16 + r;
-            const int64_t t = t0 + i;
-            if (i >= prm.offset && i < prm.offset + prm.hop && t < prm.n) store_coeff<KIND>(prm.out, obase + t, a[k]);
-        }
+        store_column<KIND>(out_c + (int64_t)prm.scale_ids[s] * prm.s_stride + rel, 256, mask, a);
         // no trailing barrier: the next scale's pre-pass writes A, whose readers all passed
         // the second barrier above; its pass 1 writes ex only after the next first barrier,
         // which every thread reaches after finishing the reads of ex just done.
@@ -478,6 +514,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
             prm.log2d = fc.level;
             prm.p_cols = (int)(fc.nc_full / kBins);
+            prm.log2p = ilog2_ceil(prm.p_cols);
             const int blocks = prm.p_cols / 16;
             prm.iters = std::min(blocks, 16);
             prm.units_per_chunk = (blocks + prm.iters - 1) / prm.iters;
@@ -493,7 +530,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             }
         } else {
             prm.src = x; prm.src_stride = x_stride; prm.src_lo = -halo_l; prm.src_hi = n + halo_r;
-            prm.log2d = 0; prm.p_cols = 16; prm.iters = 1; prm.units_per_chunk = 1;
+            prm.log2d = 0; prm.p_cols = 16; prm.log2p = 4; prm.iters = 1; prm.units_per_chunk = 1;
             const int64_t nblk = n_channels * prm.n_chunks;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
             switch (p->out_kind) {
