@@ -105,9 +105,11 @@ class CwtPlan:
                                                means.data_ptr(), self.device, st))
         return means
 
-    def execute(self, x, out=None, *, means=None, start=0, stop=None, halo_left=0, halo_right=0):
+    def execute(self, x, out=None, *, means=None, start=0, stop=None, halo_left=0, halo_right=0,
+                out_start=None):
         """Transform samples ``[start, stop)`` of every channel of ``x`` (C, N) into
-        ``out[:, :, start:stop]`` (C, S, N).  ``x`` and ``out`` are CUDA tensors."""
+        ``out[:, :, out_start : out_start + stop - start]`` (``out_start`` defaults to
+        ``start``).  ``x`` and ``out`` are CUDA tensors; ``out`` is (C, S, >= needed)."""
         torch = _torch()
         if x.dim() != 2 or not x.is_cuda or x.stride(1) != 1:
             raise ValueError("x must be a (channels, samples) CUDA tensor with unit sample stride")
@@ -120,10 +122,12 @@ class CwtPlan:
             raise ValueError("bad segment [{}, {})".format(start, stop))
         if halo_left > start or halo_right > n_all - stop:
             raise ValueError("halo reaches outside the tensor")
+        out_start = start if out_start is None else int(out_start)
         if out is None:
-            out = self.alloc_out(n_ch, n_all)
+            out = self.alloc_out(n_ch, out_start + stop - start)
         if out.dtype != self.torch_out_dtype or out.dim() != 3 or out.stride(2) != 1 \
-                or out.shape[0] != n_ch or out.shape[1] != self.n_scales or out.shape[2] != n_all:
+                or out.shape[0] != n_ch or out.shape[1] != self.n_scales \
+                or out_start < 0 or out.shape[2] < out_start + stop - start:
             raise ValueError("out must be (channels, scales, samples) of dtype %s" % self.torch_out_dtype)
         esz = x.element_size()
         osz = out.element_size()
@@ -137,7 +141,7 @@ class CwtPlan:
         _lib.check(self.lib.gcwt_execute(
             self._h, x.data_ptr() + start * esz, in_type, n_ch, stop - start, x.stride(0),
             int(halo_left), int(halo_right), mptr,
-            out.data_ptr() + start * osz, out.stride(1), out.stride(0), st))
+            out.data_ptr() + out_start * osz, out.stride(1), out.stride(0), st))
         return out
 
     def execute_host(self, x, out=None, means=None):
