@@ -240,11 +240,14 @@ def run_ours(args):
     coeffs_rank = float(nch) * n * S
     value = coeffs_rank * world / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (fused band-limited kernel) ------------------
+    # ---- roofline of the dominant kernel family -------------------------------------------
     levels = plan.levels()
     out_el = 8 if wl["output"] == "complex" else 4
-    n_banded = int((levels >= 0).sum())
+    interp_on = wl["output"] != "complex"
+    n_interp = int((levels >= 5).sum()) if interp_on else 0
+    n_banded = int((levels >= 0).sum()) - n_interp
     n_full = int((levels == -1).sum())
+    fam_scales = {"fused_interp": n_interp, "fused_banded": n_banded, "fused_full": n_full}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -252,23 +255,30 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    ms_banded, ln_banded = prof["fused_banded"]
-    n_class_launches = max(1, ln_banded)
-    # algorithmic bytes of all banded launches of one step: its output rows, plus one read of the input
-    bytes_banded_step = float(nch) * n * (n_banded * out_el + 4)
-    ach = bytes_banded_step * args.steps / (ms_banded * 1e-3) / 1e9 if ms_banded > 0 else None
-    roof = {"bound": "hbm", "kernel": "fused_banded_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
-            "launches": ln_banded, "ms_per_step": ms_banded / args.steps,
-            "share_of_step": ms_banded / ms_total if ms_total > 0 else None,
-            "bytes_per_step": bytes_banded_step,
-            "other_kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if k != "fused_banded"},
-            "whole_step": {"achieved": float(nch) * n * (S * out_el + 4) / (ms_step * 1e-3) / 1e9,
-                           "frac": float(nch) * n * (S * out_el + 4) / (ms_step * 1e-3) / 1e9 / peak}}
+    fams = {}
+    for fam, ns in fam_scales.items():
+        ms_f, ln_f = prof[fam]
+        if ns == 0 or ms_f <= 0:
+            continue
+        # algorithmic bytes of this family's launches in one step: its output rows plus one read of
+        # the (decimated) input per class; the input term is bounded by 4 B/sample per launch
+        by = float(nch) * n * (ns * out_el + 4)
+        fams[fam] = {"scales": ns, "launches_per_step": ln_f / args.steps, "ms_per_step": ms_f / args.steps,
+                     "bytes_per_step": by, "achieved_gbs": by * args.steps / (ms_f * 1e-3) / 1e9,
+                     "coeff_per_s": float(nch) * n * ns * args.steps / (ms_f * 1e-3)}
+        fams[fam]["frac"] = fams[fam]["achieved_gbs"] / peak
+    dom = max(fams, key=lambda k: fams[k]["ms_per_step"]) if fams else None
+    whole_gbs = float(nch) * n * (S * out_el + 4) / (ms_step * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": (dom + "_kernel") if dom else None,
+            "achieved": fams[dom]["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",
+            "frac": fams[dom]["frac"] if dom else None, "traffic": None, "peak_source": peak_src,
+            "share_of_step": (fams[dom]["ms_per_step"] / ms_step) if dom else None,
+            "families": fams, "mean_pyramid_ms_per_step": prof["mean+pyramid"][0] / args.steps,
+            "whole_step": {"achieved": whole_gbs, "frac": whole_gbs / peak}}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and dom:
         try:
-            roof["traffic"] = json.load(open(traffic_file)).get("fused_banded_bytes_per_launch")
+            roof["traffic"] = json.load(open(traffic_file)).get(dom + "_bytes_per_launch")
         except Exception:
             pass
 
@@ -294,8 +304,8 @@ def run_ours(args):
                        "scales": S, "fs": fs, "output": wl["output"], "parallelism": "channel-shard x%d" % world,
                        "l2_policy": "inputs (%.2f GB) and outputs (%.1f GB) per step exceed the 126 MB L2" % (
                            nch * n * 4 / 1e9, coeffs_rank * out_el / 1e9),
-                       "scale_classes": {"band_limited": n_banded, "full_spectrum": n_full,
-                                         "generic": int((levels == -2).sum())}},
+                       "scale_classes": {"band_limited_interpolated": n_interp, "band_limited": n_banded,
+                                         "full_spectrum": n_full, "generic": int((levels == -2).sum())}},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libghostcwt.so")
 F32, F64 = 0, 1
 OUT_COMPLEX, OUT_AMPLITUDE, OUT_POWER = 0, 1, 2
 FLAG_FORCE_GENERIC = 1
+FLAG_NO_INTERP = 2
 
 EXPORTS = (
     "gcwt_version", "gcwt_last_error", "gcwt_launch_count", "gcwt_plan_create",

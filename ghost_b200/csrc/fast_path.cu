@@ -99,8 +99,32 @@ static int choose_level(const gcwt_plan* p, const ScaleInfo& sc) {
 static void class_geometry(FastClass& fc) {
     const int64_t d = fc.level >= 0 ? (int64_t(1) << fc.level) : 1;
     const int64_t align = std::max<int64_t>(d, 16);
-    fc.offset = ((fc.lmax / 2 + align - 1) / align) * align;
-    fc.hop = ((fc.nc_full - (fc.lmax - 1) / 2 - fc.offset) / align) * align;
+    // interpolated classes read kInterpT coarse samples around every output: keep them valid
+    const int64_t lead = fc.interp ? (int64_t)(kInterpT / 2 - 1) << fc.log2u : 0;
+    const int64_t tail = fc.interp ? (int64_t)(kInterpT / 2 + 1) << fc.log2u : 0;
+    fc.offset = ((fc.lmax / 2 + lead + align - 1) / align) * align;
+    fc.hop = ((fc.nc_full - (fc.lmax - 1) / 2 - tail - fc.offset) / align) * align;
+}
+
+// Kaiser-windowed sinc, kInterpT taps: output at coarse position iota + phi/U is
+// sum_t c[phi][t] * p[iota + t - (T/2 - 1)].  The interpolated signal |W|^2 is band-limited
+// to a quarter of the coarse Nyquist band or less, so a wide window (beta = 14) is right.
+static void design_interpolator(int log2u, std::vector<float>& coef) {
+    const int U = 1 << log2u, T = kInterpT;
+    const double beta = 14.0, i0b = bessel_i0(beta);
+    coef.resize((size_t)U * T);
+    for (int phi = 0; phi < U; ++phi) {
+        double c[kInterpT], sum = 0.0;
+        for (int t = 0; t < T; ++t) {
+            const double tau = (double)phi / U - (double)(t - (T / 2 - 1));
+            const double r = 2.0 * tau / T;
+            const double win = std::fabs(r) < 1.0 ? bessel_i0(beta * std::sqrt(1.0 - r * r)) / i0b : 0.0;
+            const double sinc = tau == 0.0 ? 1.0 : std::sin(M_PI * tau) / (M_PI * tau);
+            c[t] = sinc * win;
+            sum += c[t];
+        }
+        for (int t = 0; t < T; ++t) coef[(size_t)phi * T + t] = (float)(c[t] / sum);
+    }
 }
 
 int fast_plan_build(gcwt_plan* p) {
@@ -126,6 +150,9 @@ int fast_plan_build(gcwt_plan* p) {
             fc.scale_ids.assign(ids.begin() + i0, ids.begin() + std::min(ids.size(), i0 + cap));
             fc.lmax = 1;
             for (int id : fc.scale_ids) fc.lmax = std::max(fc.lmax, p->scales[id].L);
+            fc.interp = level >= kInterpMinLevel && p->out_kind != GCWT_OUT_COMPLEX &&
+                        !(p->flags & GCWT_FLAG_NO_INTERP);
+            fc.log2u = level - 1;
             class_geometry(fc);
             if (fc.hop <= 0) { set_error("planner: non-positive hop"); return GCWT_ERR_ARG; }
             const int nb = level >= 0 ? kBins : kFullN;
@@ -154,6 +181,12 @@ int fast_plan_build(gcwt_plan* p) {
             }
             GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_table, sizeof(float2) * tab.size()));
             GCWT_CUDA_OK(cudaMemcpy(fc.d_table, tab.data(), sizeof(float2) * tab.size(), cudaMemcpyHostToDevice));
+            if (fc.interp) {
+                std::vector<float> coef;
+                design_interpolator(fc.log2u, coef);
+                GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_coef, sizeof(float) * coef.size()));
+                GCWT_CUDA_OK(cudaMemcpy(fc.d_coef, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
+            }
             GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_scale_ids, sizeof(int32_t) * ns));
             GCWT_CUDA_OK(cudaMemcpy(fc.d_scale_ids, fc.scale_ids.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
             p->classes.push_back(fc);
@@ -166,6 +199,7 @@ void fast_plan_free(gcwt_plan* p) {
     for (auto& fc : p->classes) {
         if (fc.d_table) cudaFree(fc.d_table);
         if (fc.d_scale_ids) cudaFree(fc.d_scale_ids);
+        if (fc.d_coef) cudaFree(fc.d_coef);
     }
     p->classes.clear();
 }
@@ -222,7 +256,9 @@ struct FusedParams {
     void* out;
     int64_t s_stride, c_stride;
     int iters;                // column blocks (16 columns each) per unit
-    int units_per_chunk;
+    int units_per_chunk;      // banded: column ranges per chunk; interp: output ranges per chunk
+    int log2u;                // interp: log2 of the coarse spacing U
+    const float* coef;        // interp: float [U][kInterpT]
 };
 
 __device__ __forceinline__ float sqrt_approx(float v) {
@@ -386,6 +422,139 @@ fused_banded_kernel(const FusedParams prm) {
     }
 }
 
+// ---------------------------------------------------------------------------- interpolated
+// Amplitude / power at level >= kInterpMinLevel.  |W_s|^2 is band-limited to +-pi/(2D), so it
+// is computed on the coarse grid i = iota * U (U = D/2: 8 columns of the pruned transform,
+// 2048 samples per chunk and scale, two scales per 16-lane pass) and brought to the full
+// rate by a kInterpT-tap polyphase FIR: ~16 instructions per output instead of ~41, which
+// moves these classes from the FP32-issue bound to the HBM bound.
+// smem: ex[4096] float2 | Zs[kMaxClassScales][256] float2 | Pc[2][kPcStride] float
+constexpr int kPcStride = kCoarse + 16;           // % 32 == 16: the two scales of a pair hit different banks
+constexpr size_t kInterpSmem = sizeof(float2) * (4096 + kMaxClassScales * kBins) + sizeof(float) * 2 * kPcStride;
+
+template <int KIND>
+__device__ __forceinline__ void interp_rows(const float* __restrict__ pc, float* __restrict__ row,
+                                            const float* __restrict__ coef, int lu, int ia, int ib,
+                                            int own_hi) {
+    // thread <-> phase phi; lanes of a warp hold consecutive phases of the same coarse interval,
+    // so the window loads are shared-memory broadcasts and the stores are contiguous.
+    const int U = 1 << lu;
+    const int tid = threadIdx.x;
+    int phi_step, n_phi_iter, phi, a, b;
+    if (U >= 256) {
+        phi = tid; phi_step = 256; n_phi_iter = U >> 8; a = ia; b = ib;
+    } else {
+        const int stripes = 256 >> lu, stripe = tid >> lu;
+        const int len = (ib - ia + stripes - 1) / stripes;
+        phi = tid & (U - 1); phi_step = U; n_phi_iter = 1;
+        a = min(ib, ia + stripe * len); b = min(ib, a + len);
+    }
+    for (int pi = 0; pi < n_phi_iter; ++pi, phi += phi_step) {
+        float c[kInterpT];
+#pragma unroll
+        for (int t = 0; t < kInterpT; ++t) c[t] = coef[phi * kInterpT + t];
+        const int b_t = min(b, (own_hi - phi + U - 1) >> lu);     // iota with iota*U + phi < own_hi
+        float w[kInterpT];
+#pragma unroll
+        for (int j = 0; j < kInterpT - 1; ++j) w[j] = pc[a - (kInterpT / 2 - 1) + j];
+        float* op = row + ((int64_t)a << lu) + phi;
+        for (int base = a; base < b_t; base += kInterpT) {
+#pragma unroll
+            for (int u = 0; u < kInterpT; ++u) {
+                // window of iota = base + u is pc[iota-4 .. iota+5], kept in w[(u + j) % T]
+                w[(u + kInterpT - 1) % kInterpT] = pc[base + u + kInterpT / 2];
+                float acc = c[0] * w[u % kInterpT];
+#pragma unroll
+                for (int j = 1; j < kInterpT; ++j) acc = fmaf(c[j], w[(u + j) % kInterpT], acc);
+                acc = fmaxf(acc, 0.f);
+                if (KIND == GCWT_OUT_AMPLITUDE) acc = sqrt_approx(acc);
+                st_pred(op, acc, (unsigned)(base + u < b_t));
+                op += U;
+            }
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 2)
+fused_interp_kernel(const FusedParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* ex = (float2*)smem_raw;
+    float2* Zs = ex + 4096;
+    float* Pc = (float*)(Zs + kMaxClassScales * kBins);
+
+    const int tid = threadIdx.x;
+    const int r = tid & 15;
+    const int g = tid >> 4;
+    const int col = r & 7;             // coarse column: chunk-local sample (8 n1 + col) * U
+    const int sidx = r >> 3;           // which scale of the pair
+
+    int64_t bid = blockIdx.x;
+    const int split = (int)(bid % prm.units_per_chunk); bid /= prm.units_per_chunk;
+    const int64_t q = bid % prm.n_chunks;
+    const int64_t c = bid / prm.n_chunks;
+    const int64_t t0 = q * prm.hop - prm.offset;
+
+    // this block's share of the chunk's owned output window, in coarse intervals
+    const int lu = prm.log2u;
+    const int own_lo = (int)prm.offset;
+    const int own_hi = (int)min(prm.offset + prm.hop, prm.n - t0);
+    const int io_lo = own_lo >> lu, io_hi = (own_hi + (1 << lu) - 1) >> lu;
+    const int len = (io_hi - io_lo + prm.units_per_chunk - 1) / prm.units_per_chunk;
+    const int ia = io_lo + split * len, ib = min(io_hi, ia + len);
+    if (ia >= ib) return;
+
+    {   // (1) forward FFT of the decimated chunk, (2) multiply by every scale's response
+        const float* src = (const float*)prm.src + c * prm.src_stride - prm.src_lo;
+        const int64_t i0 = t0 >> prm.log2d;
+        for (int i = tid; i < kChunkDec; i += 256) {
+            const int64_t u = i0 + i;
+            float v = 0.f;
+            if (u >= prm.src_lo && u < prm.src_hi) v = src[u];
+            ex[i] = make_float2(v, 0.f);
+        }
+        __syncthreads();
+        float2* Y = smem_fft_forward<5>(ex, ex + kChunkDec);
+        const float2 y = Y[tid];
+        for (int s = 0; s < prm.n_scales; ++s) Zs[s * kBins + tid] = cmul(y, prm.table[s * kBins + tid]);
+    }
+    float2 tw[16], R[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        tw[k] = expipi((float)(2 * g * k) * (1.0f / 256.0f));
+        R[k] = expipi((float)((2 * (g + 16 * k) * col) & 4095) * (1.0f / 2048.0f));   // e^{2 pi i m col / 2048}
+    }
+    __syncthreads();
+
+    float* const out_c = (float*)prm.out + c * prm.c_stride + t0;
+    for (int pair = 0; pair < prm.n_scales; pair += 2) {
+        const int s = min(pair + sidx, prm.n_scales - 1);
+        float2 a[16];
+        const float2* z = Zs + s * kBins + g;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = cmul(z[16 * i], R[i]);
+        dft16<+1>(a);
+        float2* e = ex + (g * 16) * 16 + r;
+        e[0] = a[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
+        __syncthreads();
+        const float2* e2 = ex + g * 16 + r;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
+        dft16<+1>(a);
+        float* pc = Pc + sidx * kPcStride + g * 8 + col;          // iota = (g + 16 k) * 8 + col
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pc[k * 128] = a[k].x * a[k].x + a[k].y * a[k].y;
+        __syncthreads();
+        // (3) polyphase interpolation + epilogue for the one or two scales of the pair
+        for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl)
+            interp_rows<KIND>(Pc + sl * kPcStride, out_c + (int64_t)prm.scale_ids[pair + sl] * prm.s_stride,
+                              prm.coef, lu, ia, ib, own_hi);
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------- full spectrum
 // smem: Yf[4096] | A[4096] | ex[4096]
 constexpr size_t kFullSmem = sizeof(float2) * 3 * 4096;
@@ -499,7 +668,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
 
     // ---- fused kernels ---------------------------------------------------------------
     for (const FastClass& fc : p->classes) {
-        const int sp = prof_begin(p, fc.level >= 0 ? 2 : 1, st);
+        const int sp = prof_begin(p, fc.level < 0 ? 1 : (fc.interp ? 4 : 2), st);
         FusedParams prm;
         prm.means = d_means;
         prm.offset = fc.offset; prm.hop = fc.hop; prm.n = n;
@@ -509,7 +678,26 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prm.table = fc.d_table;
         prm.out = out; prm.s_stride = s_stride; prm.c_stride = c_stride;
         prm.inv_nc = 1.0f / (float)fc.nc_full;
-        if (fc.level >= 0) {
+        prm.log2u = fc.log2u; prm.coef = fc.d_coef;
+        if (fc.level >= 0 && fc.interp) {
+            const LevelGeom& g = lv[fc.level];
+            prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
+            prm.log2d = fc.level;
+            prm.p_cols = (int)(fc.nc_full / kBins);
+            prm.log2p = ilog2_ceil(prm.p_cols);
+            prm.iters = 1;
+            // enough blocks for ~6 waves of 2 x 148, but at least ~64 coarse intervals per block
+            const int64_t chunks = n_channels * prm.n_chunks;
+            int64_t splits = (1776 + chunks - 1) / chunks;
+            splits = std::max<int64_t>(1, std::min<int64_t>(splits, 24));
+            prm.units_per_chunk = (int)splits;
+            const int64_t nblk = chunks * splits;
+            if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
+            if (p->out_kind == GCWT_OUT_AMPLITUDE)
+                fused_interp_kernel<GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
+            else
+                fused_interp_kernel<GCWT_OUT_POWER><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
+        } else if (fc.level >= 0) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
             prm.log2d = fc.level;
@@ -556,6 +744,8 @@ static int set_smem_attrs() {
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_banded_kernel<GCWT_OUT_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_banded_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_banded_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_full_kernel<TIn, GCWT_OUT_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_full_kernel<TIn, GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_full_kernel<TIn, GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem));

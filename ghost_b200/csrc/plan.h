@@ -12,6 +12,9 @@ constexpr int kChunkDec = 1024;     // chunk length in decimated samples (forwar
 constexpr int kFullN = 4096;        // chunk length of the full-spectrum fused kernel
 constexpr int kMaxClassScales = 16; // scales handled by one fused launch (shared-memory table)
 constexpr int kMinFastLevel = 2;    // P = kChunkDec * 2^level / kBins must be >= 16
+constexpr int kInterpT = 10;        // taps of the polyphase interpolator (amplitude / power output)
+constexpr int kInterpMinLevel = 5;  // interpolated classes: coarse spacing U = 2^(level-1) >= 16
+constexpr int kCoarse = 2048;       // coarse |W|^2 samples per chunk and scale (8 columns x 256)
 constexpr int kHalfbandT = 19;      // half-band taps run from -T..T
 constexpr int kHalfbandOdd = (kHalfbandT + 1) / 2;
 
@@ -34,6 +37,11 @@ struct FastClass {
     // full:   float2 [n][kFullN] (response incl. 1/kFullN)
     float2* d_table = nullptr;
     int32_t* d_scale_ids = nullptr;
+    // amplitude / power at level >= kInterpMinLevel: |W|^2 on a grid of spacing U = 2^log2u,
+    // then a kInterpT-tap polyphase interpolator; d_coef is float [U][kInterpT]
+    bool interp = false;
+    int log2u = 0;
+    float* d_coef = nullptr;
 };
 
 struct Workspace {
@@ -62,8 +70,8 @@ struct gcwt_plan {
     bool profile = false;
     struct Span { cudaEvent_t a, b; int kind; int launches; };
     std::vector<Span> spans;
-    double prof_ms[GCWT_PROFILE_KINDS] = {0, 0, 0, 0};
-    int64_t prof_launches[GCWT_PROFILE_KINDS] = {0, 0, 0, 0};
+    double prof_ms[GCWT_PROFILE_KINDS] = {0, 0, 0, 0, 0};
+    int64_t prof_launches[GCWT_PROFILE_KINDS] = {0, 0, 0, 0, 0};
     double* d_means = nullptr;              // internal per-channel means
     int64_t means_cap = 0;
 };

@@ -38,7 +38,7 @@ class CwtPlan:
     """Device tables for one set of scales."""
 
     def __init__(self, lengths, k_first, n_terms, terms, *, dtype=np.float32, output="amplitude",
-                 device=0, force_generic=False, band_tol=0.0):
+                 device=0, force_generic=False, no_interp=False, band_tol=0.0):
         dtype = np.dtype(dtype)
         if dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
             raise ValueError("dtype must be float32 or float64 but got {}".format(dtype))
@@ -62,7 +62,7 @@ class CwtPlan:
         desc.compute_type = _lib.F32 if dtype == np.float32 else _lib.F64
         desc.out_kind = OUT_KINDS[output]
         desc.device = self.device
-        desc.flags = _lib.FLAG_FORCE_GENERIC if force_generic else 0
+        desc.flags = (_lib.FLAG_FORCE_GENERIC if force_generic else 0) | (_lib.FLAG_NO_INTERP if no_interp else 0)
         desc.band_tol = float(band_tol)
         handle = C.c_void_p()
         _lib.check(self.lib.gcwt_plan_create(C.byref(handle), C.byref(desc)))
@@ -168,15 +168,15 @@ class CwtPlan:
                                               mptr, out.ctypes.data, n, n * self.n_scales))
         return out
 
-    PROFILE_KINDS = ("mean+pyramid", "fused_full", "fused_banded", "generic")
+    PROFILE_KINDS = ("mean+pyramid", "fused_full", "fused_banded", "generic", "fused_interp")
 
     def profile(self, on=True):
         _lib.check(self.lib.gcwt_profile_enable(self._h, 1 if on else 0))
 
     def profile_read(self, reset=True):
         """{family: (milliseconds, launches)} accumulated since the last reset."""
-        ms = (C.c_double * 4)()
-        ln = (C.c_int64 * 4)()
+        ms = (C.c_double * 5)()
+        ln = (C.c_int64 * 5)()
         _lib.check(self.lib.gcwt_profile_read(self._h, ms, ln, 1 if reset else 0))
         return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(self.PROFILE_KINDS)}
 

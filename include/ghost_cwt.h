@@ -53,6 +53,8 @@ extern "C" {
 
 /* plan flags */
 #define GCWT_FLAG_FORCE_GENERIC 1   /* fp32 only: skip the band-limited fast path */
+#define GCWT_FLAG_NO_INTERP     2   /* fp32 amplitude/power: compute every output sample with the pruned
+                                       inverse FFT instead of coarse grid + polyphase interpolation */
 
 typedef struct gcwt_plan gcwt_plan;
 
@@ -136,8 +138,9 @@ size_t gcwt_plan_workspace_bytes(const gcwt_plan *plan);
  * gcwt_execute brackets every launch group with CUDA events on the launch stream.
  * gcwt_profile_read synchronises those events and returns accumulated milliseconds and
  * launch counts for: [0] mean + decimation pyramid, [1] fused full-spectrum kernel,
- * [2] fused band-limited kernel, [3] generic global-memory path. */
-#define GCWT_PROFILE_KINDS 4
+ * [2] fused band-limited kernel, [3] generic global-memory path, [4] fused band-limited
+ * kernel with coarse grid + polyphase interpolation. */
+#define GCWT_PROFILE_KINDS 5
 int gcwt_profile_enable(gcwt_plan *plan, int32_t on);
 int gcwt_profile_read(gcwt_plan *plan, double *ms_out, int64_t *launches_out, int32_t reset);
 

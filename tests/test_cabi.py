@@ -36,6 +36,7 @@ def test_constants_match_header():
     assert int(defs["GCWT_OUT_AMPLITUDE"]) == _lib.OUT_AMPLITUDE
     assert int(defs["GCWT_OUT_POWER"]) == _lib.OUT_POWER
     assert int(defs["GCWT_FLAG_FORCE_GENERIC"]) == _lib.FLAG_FORCE_GENERIC
+    assert int(defs["GCWT_FLAG_NO_INTERP"]) == _lib.FLAG_NO_INTERP
 
 
 def test_argument_errors_without_device():
