@@ -162,6 +162,7 @@ int gcwt_plan_destroy(gcwt_plan* p) {
     if (p->d_terms) cudaFree(p->d_terms);
     if (p->ws.ptr) cudaFree(p->ws.ptr);
     if (p->d_means) cudaFree(p->d_means);
+    if (p->d_twiddle) cudaFree(p->d_twiddle);
     delete p;
     return GCWT_OK;
 }

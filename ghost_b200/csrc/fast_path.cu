@@ -32,6 +32,9 @@ constexpr int kMaxFullScales = 64;
 constexpr double kMaxHaloFrac = 0.45;   // (L-1) / chunk must stay below this
 
 __constant__ double c_halfband[kHalfbandOdd];
+// polyphase taps for the small coarse spacings U = 2, 4, 8 (constant-bank operands of the FMAs)
+constexpr int kSmallCoef = (2 + 4 + 8) * kInterpT;
+__constant__ float c_interp_small[kSmallCoef];
 
 // ============================================================================ planner
 static double bessel_i0(double x) {
@@ -127,9 +130,29 @@ static void design_interpolator(int log2u, std::vector<float>& coef) {
     }
 }
 
+static int upload_constants(const gcwt_plan* p) {
+    GCWT_CUDA_OK(cudaMemcpyToSymbol(c_halfband, p->halfband_odd, sizeof(double) * kHalfbandOdd));
+    std::vector<float> all, part;
+    for (int lu = 1; lu <= 3; ++lu) {
+        design_interpolator(lu, part);
+        all.insert(all.end(), part.begin(), part.end());
+    }
+    GCWT_CUDA_OK(cudaMemcpyToSymbol(c_interp_small, all.data(), sizeof(float) * kSmallCoef));
+    return GCWT_OK;
+}
+
 int fast_plan_build(gcwt_plan* p) {
     design_halfband(p->halfband_odd);
-    GCWT_CUDA_OK(cudaMemcpyToSymbol(c_halfband, p->halfband_odd, sizeof(double) * kHalfbandOdd));
+    { int rc = upload_constants(p); if (rc) return rc; }
+    {
+        std::vector<float2> tw(kFullN);
+        for (int k = 0; k < kFullN; ++k) {
+            const double a = -2.0 * M_PI * (double)k / (double)kFullN;
+            tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        GCWT_CUDA_OK(cudaMalloc((void**)&p->d_twiddle, sizeof(float2) * kFullN));
+        GCWT_CUDA_OK(cudaMemcpy(p->d_twiddle, tw.data(), sizeof(float2) * kFullN, cudaMemcpyHostToDevice));
+    }
     std::map<int, std::vector<int>> by_level;
     p->max_level = 0;
     for (int s = 0; s < p->n_scales; ++s) {
@@ -259,6 +282,7 @@ struct FusedParams {
     int units_per_chunk;      // banded: column ranges per chunk; interp: output ranges per chunk
     int log2u;                // interp: log2 of the coarse spacing U
     const float* coef;        // interp: float [U][kInterpT]
+    const float2* twf;        // e^{-2 pi i k / 4096}
 };
 
 __device__ __forceinline__ float sqrt_approx(float v) {
@@ -303,23 +327,25 @@ __device__ __forceinline__ unsigned valid_mask(int rel, int sh, int lo, int hi) 
     return k_hi > k_lo ? (((1u << k_hi) - 1u) & ~((1u << k_lo) - 1u)) : 0u;
 }
 
-// In-place-ish radix-4 Stockham FFT in shared memory, forward sign, N = 4^PASSES points,
-// 256 threads.  Result lands in `a` when PASSES is even, in `b` when odd.
+// Radix-4 Stockham FFT in shared memory, forward sign, N = 4^PASSES <= 1024 points, 256
+// threads, twiddles from the 4096-entry table `tw`.  Result lands in `a` when PASSES is even,
+// in `b` when odd.
 template <int PASSES>
-__device__ __forceinline__ float2* smem_fft_forward(float2* a, float2* b) {
+__device__ __forceinline__ float2* smem_fft_forward(float2* a, float2* b, const float2* __restrict__ tw) {
     constexpr int N = 1 << (2 * PASSES);
     constexpr int M = N / 4;
     int ns = 1;
 #pragma unroll 1
     for (int pass = 0; pass < PASSES; ++pass) {
+        const int tstep = (kFullN / 4) / ns;                 // table stride of e^{-2 pi i / (4 ns)}
         for (int j = threadIdx.x; j < M; j += 256) {
             const int k = j & (ns - 1);
             float2 v0 = a[j], v1 = a[j + M], v2 = a[j + 2 * M], v3 = a[j + 3 * M];
             if (ns > 1) {
-                const float ang = -2.0f * (float)k / (float)(ns * 4);
-                v1 = cmul(v1, expipi(ang));
-                v2 = cmul(v2, expipi(2.0f * ang));
-                v3 = cmul(v3, expipi(3.0f * ang));
+                const int idx = k * tstep;
+                v1 = cmul(v1, __ldg(tw + idx));
+                v2 = cmul(v2, __ldg(tw + 2 * idx));
+                v3 = cmul(v3, __ldg(tw + 3 * idx));
             }
             dft4<-1>(v0, v1, v2, v3);
             const int j0 = ((j - k) << 2) + k;
@@ -330,6 +356,40 @@ __device__ __forceinline__ float2* smem_fft_forward(float2* a, float2* b) {
         ns <<= 2;
     }
     return a;
+}
+
+// 4096-point forward FFT as three radix-16 Stockham passes, one butterfly per thread and
+// pass.  Input in `x`, result in `y`; `y` needs 256 elements of slack behind it (the first
+// pass writes with a pad of one element per 16 to stay free of bank conflicts).
+__device__ __forceinline__ void smem_fft4096_forward(float2* x, float2* y, const float2* __restrict__ tw) {
+    const int tid = threadIdx.x;
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = x[tid + 256 * r];
+    dft16<-1>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) y[17 * tid + r] = v[r];                      // position 16 tid + r, padded
+    __syncthreads();
+    {
+        const int k = tid & 15;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = y[tid + 256 * r + (tid >> 4) + 16 * r];
+#pragma unroll
+        for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(tw + r * k * 16));
+        dft16<-1>(v);
+        const int j0 = ((tid - k) << 4) + k;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[j0 + 16 * r] = v[r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = x[tid + 256 * r];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(tw + r * tid));
+    dft16<-1>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) y[tid + 256 * r] = v[r];
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------- banded
@@ -365,7 +425,7 @@ fused_banded_kernel(const FusedParams prm) {
             ex[i] = make_float2(v, 0.f);
         }
         __syncthreads();
-        float2* Y = smem_fft_forward<5>(ex, ex + kChunkDec);     // 1024 points
+        float2* Y = smem_fft_forward<5>(ex, ex + kChunkDec, prm.twf);     // 1024 points
         // ---- (2) multiply by every scale's response (bins 0..255) ---------------
         const float2 y = Y[tid];
         for (int s = 0; s < prm.n_scales; ++s) Zs[s * kBins + tid] = cmul(y, prm.table[s * kBins + tid]);
@@ -475,6 +535,45 @@ __device__ __forceinline__ void interp_rows(const float* __restrict__ pc, float*
     }
 }
 
+// Small coarse spacings (U = 2, 4, 8): thread <-> coarse interval, all U phases per thread from
+// one register window; taps come from the constant bank; U consecutive outputs leave as one
+// or two 128-bit stores (the launcher guarantees 16-byte aligned rows).
+template <int KIND, int LU>
+__device__ __forceinline__ void interp_rows_small(const float* __restrict__ pc, float* __restrict__ row,
+                                                  int ia, int ib, int own_hi) {
+    constexpr int U = 1 << LU;
+    constexpr int COFF = (LU == 1) ? 0 : (LU == 2 ? 2 * kInterpT : 6 * kInterpT);
+    for (int iota = ia + (int)threadIdx.x; iota < ib; iota += 256) {
+        float w[kInterpT];
+#pragma unroll
+        for (int j = 0; j < kInterpT; ++j) w[j] = pc[iota - (kInterpT / 2 - 1) + j];
+        float o[U];
+        o[0] = w[kInterpT / 2 - 1];                               // phase 0 sits on a coarse sample
+#pragma unroll
+        for (int phi = 1; phi < U; ++phi) {
+            float acc = c_interp_small[COFF + phi * kInterpT] * w[0];
+#pragma unroll
+            for (int j = 1; j < kInterpT; ++j) acc = fmaf(c_interp_small[COFF + phi * kInterpT + j], w[j], acc);
+            o[phi] = fmaxf(acc, 0.f);
+        }
+        if (KIND == GCWT_OUT_AMPLITUDE) {
+#pragma unroll
+            for (int phi = 0; phi < U; ++phi) o[phi] = sqrt_approx(o[phi]);
+        }
+        float* op = row + (int64_t)iota * U;
+        if ((iota + 1) * U <= own_hi) {
+            if (U == 2) *(float2*)op = make_float2(o[0], o[1]);
+            else {
+#pragma unroll
+                for (int v = 0; v < U / 4; ++v) ((float4*)op)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int phi = 0; phi < U; ++phi) if (iota * U + phi < own_hi) op[phi] = o[phi];
+        }
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256, 2)
 fused_interp_kernel(const FusedParams prm) {
@@ -514,7 +613,7 @@ fused_interp_kernel(const FusedParams prm) {
             ex[i] = make_float2(v, 0.f);
         }
         __syncthreads();
-        float2* Y = smem_fft_forward<5>(ex, ex + kChunkDec);
+        float2* Y = smem_fft_forward<5>(ex, ex + kChunkDec, prm.twf);
         const float2 y = Y[tid];
         for (int s = 0; s < prm.n_scales; ++s) Zs[s * kBins + tid] = cmul(y, prm.table[s * kBins + tid]);
     }
@@ -548,9 +647,14 @@ fused_interp_kernel(const FusedParams prm) {
         for (int k = 0; k < 16; ++k) pc[k * 128] = a[k].x * a[k].x + a[k].y * a[k].y;
         __syncthreads();
         // (3) polyphase interpolation + epilogue for the one or two scales of the pair
-        for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl)
-            interp_rows<KIND>(Pc + sl * kPcStride, out_c + (int64_t)prm.scale_ids[pair + sl] * prm.s_stride,
-                              prm.coef, lu, ia, ib, own_hi);
+        for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl) {
+            const float* pcs = Pc + sl * kPcStride;
+            float* row = out_c + (int64_t)prm.scale_ids[pair + sl] * prm.s_stride;
+            if (lu >= 4) interp_rows<KIND>(pcs, row, prm.coef, lu, ia, ib, own_hi);
+            else if (lu == 3) interp_rows_small<KIND, 3>(pcs, row, ia, ib, own_hi);
+            else if (lu == 2) interp_rows_small<KIND, 2>(pcs, row, ia, ib, own_hi);
+            else interp_rows_small<KIND, 1>(pcs, row, ia, ib, own_hi);
+        }
         __syncthreads();
     }
 }
@@ -563,9 +667,9 @@ template <typename TIn, int KIND>
 __global__ void __launch_bounds__(256, 2)
 fused_full_kernel(const FusedParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* Yf = (float2*)smem_raw;
-    float2* A = Yf + kFullN;
-    float2* ex = A + kFullN;
+    float2* Yf = (float2*)smem_raw;      // order matters: the forward FFT's padded pass spills 2 KB into ex
+    float2* ex = Yf + kFullN;
+    float2* A = ex + kFullN;
 
     const int tid = threadIdx.x;
     const int r = tid & 15;
@@ -581,10 +685,10 @@ fused_full_kernel(const FusedParams prm) {
             const int64_t u = t0 + i;
             float v = 0.f;
             if (u >= prm.src_lo && u < prm.src_hi) v = (float)((double)src[u] - mu);
-            Yf[i] = make_float2(v, 0.f);
+            A[i] = make_float2(v, 0.f);
         }
         __syncthreads();
-        smem_fft_forward<6>(Yf, A);                              // even pass count: result in Yf
+        smem_fft4096_forward(A, Yf, prm.twf);
     }
     float2 tw[16], tw4k[16];
 #pragma unroll
@@ -669,6 +773,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
     // ---- fused kernels ---------------------------------------------------------------
     for (const FastClass& fc : p->classes) {
         const int sp = prof_begin(p, fc.level < 0 ? 1 : (fc.interp ? 4 : 2), st);
+        // (an interpolated class that falls back to the direct kernel is still booked as [4])
         FusedParams prm;
         prm.means = d_means;
         prm.offset = fc.offset; prm.hop = fc.hop; prm.n = n;
@@ -678,8 +783,10 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prm.table = fc.d_table;
         prm.out = out; prm.s_stride = s_stride; prm.c_stride = c_stride;
         prm.inv_nc = 1.0f / (float)fc.nc_full;
-        prm.log2u = fc.log2u; prm.coef = fc.d_coef;
-        if (fc.level >= 0 && fc.interp) {
+        prm.log2u = fc.log2u; prm.coef = fc.d_coef; prm.twf = p->d_twiddle;
+        // the small-spacing interpolator writes 128-bit vectors: rows must be 16-byte aligned
+        const bool rows_aligned = ((uintptr_t)out % 16 == 0) && (s_stride % 4 == 0) && (c_stride % 4 == 0);
+        if (fc.level >= 0 && fc.interp && (fc.log2u >= 4 || rows_aligned)) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
             prm.log2d = fc.level;
@@ -689,7 +796,10 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             // enough blocks for ~6 waves of 2 x 148, but at least ~64 coarse intervals per block
             const int64_t chunks = n_channels * prm.n_chunks;
             int64_t splits = (1776 + chunks - 1) / chunks;
-            splits = std::max<int64_t>(1, std::min<int64_t>(splits, 24));
+            // every block repeats the chunk's forward FFT and coarse transforms: only split
+            // when the interpolation work per block stays several times larger
+            splits = std::max<int64_t>(1, std::min<int64_t>(splits, std::max<int64_t>(1, (int64_t(1) << fc.level) / 32)));
+            splits = std::min<int64_t>(splits, 24);
             prm.units_per_chunk = (int)splits;
             const int64_t nblk = chunks * splits;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
@@ -759,8 +869,9 @@ int fast_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, i
     if (!g_attr_done[slot]) {
         int rc = in_type == GCWT_F32 ? set_smem_attrs<float>() : set_smem_attrs<double>();
         if (rc) return rc;
-        // constant memory is per device: (re)load the half-band taps
-        GCWT_CUDA_OK(cudaMemcpyToSymbol(c_halfband, p->halfband_odd, sizeof(double) * kHalfbandOdd));
+        // constant memory is per device: (re)load the filter taps
+        rc = upload_constants(p);
+        if (rc) return rc;
         g_attr_done[slot] = true;
     }
     if (in_type == GCWT_F32)

@@ -13,7 +13,7 @@ constexpr int kFullN = 4096;        // chunk length of the full-spectrum fused k
 constexpr int kMaxClassScales = 16; // scales handled by one fused launch (shared-memory table)
 constexpr int kMinFastLevel = 2;    // P = kChunkDec * 2^level / kBins must be >= 16
 constexpr int kInterpT = 10;        // taps of the polyphase interpolator (amplitude / power output)
-constexpr int kInterpMinLevel = 5;  // interpolated classes: coarse spacing U = 2^(level-1) >= 16
+constexpr int kInterpMinLevel = 3;  // interpolated classes: coarse spacing U = 2^(level-1) >= 4
 constexpr int kCoarse = 2048;       // coarse |W|^2 samples per chunk and scale (8 columns x 256)
 constexpr int kHalfbandT = 19;      // half-band taps run from -T..T
 constexpr int kHalfbandOdd = (kHalfbandT + 1) / 2;
@@ -72,6 +72,7 @@ struct gcwt_plan {
     std::vector<Span> spans;
     double prof_ms[GCWT_PROFILE_KINDS] = {0, 0, 0, 0, 0};
     int64_t prof_launches[GCWT_PROFILE_KINDS] = {0, 0, 0, 0, 0};
+    float2* d_twiddle = nullptr;            // e^{-2 pi i k / 4096}, k < 4096 (forward FFTs of the fused kernels)
     double* d_means = nullptr;              // internal per-channel means
     int64_t means_cap = 0;
 };
