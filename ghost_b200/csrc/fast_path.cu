@@ -87,6 +87,26 @@ static bool band_fits(const gcwt_plan* p, const ScaleInfo& sc, int level, double
     return (1.0 - e_in / e_tot) < p->band_tol * p->band_tol;
 }
 
+// Full-spectrum kernel: how many 256-bin blocks of the 4096-point grid does the filter occupy?
+// One-sided filters leave the upper blocks empty (below band_tol in energy), and the kernel's
+// radix-16 pre-pass over the 16 aliases of a bin is pruned accordingly.
+static int full_extent(const gcwt_plan* p, const ScaleInfo& sc) {
+    const double* X = p->terms.data() + sc.term_off;
+    double e_tot = 0.0;
+    for (int t = 0; t < sc.n_terms; ++t) e_tot += X[t] * X[t];
+    e_tot *= (double)kFullN / (double)sc.L;
+    double e_in = 0.0;
+    int m = 0;
+    for (int nmu = 2; nmu <= 8; nmu *= 2) {
+        for (; m < nmu * kBins; ++m) {
+            const double g = morse_response(m, kFullN, sc.L, sc.k_first, sc.n_terms, X);
+            e_in += g * g;
+        }
+        if ((1.0 - e_in / e_tot) < p->band_tol * p->band_tol) return nmu;
+    }
+    return 16;
+}
+
 static int choose_level(const gcwt_plan* p, const ScaleInfo& sc) {
     if (!(p->flags & GCWT_FLAG_FORCE_GENERIC)) {
         int lo = kMinFastLevel;
@@ -210,6 +230,11 @@ int fast_plan_build(gcwt_plan* p) {
                 GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_coef, sizeof(float) * coef.size()));
                 GCWT_CUDA_OK(cudaMemcpy(fc.d_coef, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
             }
+            if (level < 0) {
+                for (int id : fc.scale_ids) fc.scale_nmu.push_back(full_extent(p, p->scales[id]));
+                GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_scale_nmu, sizeof(int32_t) * ns));
+                GCWT_CUDA_OK(cudaMemcpy(fc.d_scale_nmu, fc.scale_nmu.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
+            }
             GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_scale_ids, sizeof(int32_t) * ns));
             GCWT_CUDA_OK(cudaMemcpy(fc.d_scale_ids, fc.scale_ids.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
             p->classes.push_back(fc);
@@ -223,6 +248,7 @@ void fast_plan_free(gcwt_plan* p) {
         if (fc.d_table) cudaFree(fc.d_table);
         if (fc.d_scale_ids) cudaFree(fc.d_scale_ids);
         if (fc.d_coef) cudaFree(fc.d_coef);
+        if (fc.d_scale_nmu) cudaFree(fc.d_scale_nmu);
     }
     p->classes.clear();
 }
@@ -283,6 +309,7 @@ struct FusedParams {
     int log2u;                // interp: log2 of the coarse spacing U
     const float* coef;        // interp: float [U][kInterpT]
     const float2* twf;        // e^{-2 pi i k / 4096}
+    const int32_t* scale_nmu; // full: occupied 256-bin blocks per scale
 };
 
 __device__ __forceinline__ float sqrt_approx(float v) {
@@ -663,6 +690,21 @@ fused_interp_kernel(const FusedParams prm) {
 // smem: Yf[4096] | A[4096] | ex[4096]
 constexpr size_t kFullSmem = sizeof(float2) * 3 * 4096;
 
+// radix-16 over the aliases m' + 256 mu of spectrum bin m' = tid, pruned to the first NMU
+// aliases (the others are empty for a filter that occupies only NMU blocks of 256 bins)
+template <int NMU>
+__device__ __forceinline__ void full_prepass(const float2* __restrict__ Yf, const float2* __restrict__ tab,
+                                             float2* __restrict__ A, const float2* tw4k) {
+    const int tid = threadIdx.x;
+    float2 a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        a[k] = (k < NMU) ? cmul(Yf[tid + 256 * k], __ldg(tab + 256 * k)) : make_float2(0.f, 0.f);
+    dft16<+1>(a);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) A[tid * 16 + (k ^ (tid & 15))] = k ? cmul(a[k], tw4k[k]) : a[k];
+}
+
 template <typename TIn, int KIND>
 __global__ void __launch_bounds__(256, 2)
 fused_full_kernel(const FusedParams prm) {
@@ -702,13 +744,12 @@ fused_full_kernel(const FusedParams prm) {
     OutT* const out_c = (OutT*)prm.out + c * prm.c_stride + t0;
     for (int s = 0; s < prm.n_scales; ++s) {
         float2 a[16];
-        // pre-pass: radix-16 over mu for spectrum bin m' = tid
         const float2* tab = prm.table + (int64_t)s * kFullN + tid;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = cmul(Yf[tid + 256 * k], tab[256 * k]);
-        dft16<+1>(a);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) A[tid * 16 + (k ^ (tid & 15))] = k ? cmul(a[k], tw4k[k]) : a[k];
+        const int nmu = prm.scale_nmu[s];
+        if (nmu == 2) full_prepass<2>(Yf, tab, A, tw4k);
+        else if (nmu == 4) full_prepass<4>(Yf, tab, A, tw4k);
+        else if (nmu == 8) full_prepass<8>(Yf, tab, A, tw4k);
+        else full_prepass<16>(Yf, tab, A, tw4k);
         __syncthreads();
         // pass 1 of the 256-point transforms (16 columns)
 #pragma unroll
@@ -731,6 +772,25 @@ fused_full_kernel(const FusedParams prm) {
 }
 
 // ============================================================================ driver
+template <typename TIn, int KIND>
+static void launch_full_kind(unsigned nblk, cudaStream_t st, const FusedParams& prm) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaFuncSetAttribute(fused_full_kernel<TIn, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem);
+        attr_set[dev & 63] = true;
+    }
+    fused_full_kernel<TIn, KIND><<<nblk, 256, kFullSmem, st>>>(prm);
+}
+
+template <typename TIn>
+static void launch_full(int kind, unsigned nblk, cudaStream_t st, const FusedParams& prm) {
+    if (kind == GCWT_OUT_COMPLEX) launch_full_kind<TIn, GCWT_OUT_COMPLEX>(nblk, st, prm);
+    else if (kind == GCWT_OUT_AMPLITUDE) launch_full_kind<TIn, GCWT_OUT_AMPLITUDE>(nblk, st, prm);
+    else launch_full_kind<TIn, GCWT_OUT_POWER>(nblk, st, prm);
+}
+
 struct LevelGeom { int64_t lo, hi, len, stride; float* ptr; };
 
 template <typename TIn>
@@ -783,7 +843,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prm.table = fc.d_table;
         prm.out = out; prm.s_stride = s_stride; prm.c_stride = c_stride;
         prm.inv_nc = 1.0f / (float)fc.nc_full;
-        prm.log2u = fc.log2u; prm.coef = fc.d_coef; prm.twf = p->d_twiddle;
+        prm.log2u = fc.log2u; prm.coef = fc.d_coef; prm.twf = p->d_twiddle; prm.scale_nmu = fc.d_scale_nmu;
         // the small-spacing interpolator writes 128-bit vectors: rows must be 16-byte aligned
         const bool rows_aligned = ((uintptr_t)out % 16 == 0) && (s_stride % 4 == 0) && (c_stride % 4 == 0);
         if (fc.level >= 0 && fc.interp && (fc.log2u >= 4 || rows_aligned)) {
@@ -831,14 +891,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.log2d = 0; prm.p_cols = 16; prm.log2p = 4; prm.iters = 1; prm.units_per_chunk = 1;
             const int64_t nblk = n_channels * prm.n_chunks;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
-            switch (p->out_kind) {
-                case GCWT_OUT_COMPLEX:
-                    fused_full_kernel<TIn, GCWT_OUT_COMPLEX><<<(unsigned)nblk, 256, kFullSmem, st>>>(prm); break;
-                case GCWT_OUT_AMPLITUDE:
-                    fused_full_kernel<TIn, GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kFullSmem, st>>>(prm); break;
-                default:
-                    fused_full_kernel<TIn, GCWT_OUT_POWER><<<(unsigned)nblk, 256, kFullSmem, st>>>(prm); break;
-            }
+            launch_full<TIn>(p->out_kind, (unsigned)nblk, st, prm);
         }
         count_launch();
         prof_end(p, sp, st);
@@ -856,9 +909,6 @@ static int set_smem_attrs() {
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_banded_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_full_kernel<TIn, GCWT_OUT_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_full_kernel<TIn, GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_full_kernel<TIn, GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem));
     return GCWT_OK;
 }
 

@@ -39,6 +39,8 @@ struct FastClass {
     int32_t* d_scale_ids = nullptr;
     // amplitude / power at level >= kInterpMinLevel: |W|^2 on a grid of spacing U = 2^log2u,
     // then a kInterpT-tap polyphase interpolator; d_coef is float [U][kInterpT]
+    std::vector<int> scale_nmu;     // full-spectrum kernel: occupied 256-bin blocks per scale (2, 4, 8, 16)
+    int32_t* d_scale_nmu = nullptr;
     bool interp = false;
     int log2u = 0;
     float* d_coef = nullptr;
