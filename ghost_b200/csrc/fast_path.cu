@@ -31,7 +31,7 @@ constexpr int kMaxFastLevel = 14;       // chunk of 1024 << 14 samples: phases s
 constexpr int kMaxFullScales = 64;
 constexpr double kMaxHaloFrac = 0.45;   // (L-1) / chunk must stay below this
 
-__constant__ double c_halfband[kHalfbandOdd];
+__constant__ float c_halfband[kHalfbandOdd];
 // polyphase taps for the small coarse spacings U = 2, 4, 8 (constant-bank operands of the FMAs)
 constexpr int kSmallCoef = (2 + 4 + 8) * kInterpT;
 __constant__ float c_interp_small[kSmallCoef];
@@ -66,8 +66,8 @@ static void design_halfband(double* odd /*kHalfbandOdd*/) {
 }
 
 static double halfband_gain(const double* odd, double theta) {
-    double g = 0.5;
-    for (int k = 0; k < kHalfbandOdd; ++k) g += 2.0 * odd[k] * std::cos((2 * k + 1) * theta);
+    double g = 0.5;                       // the device applies the taps rounded to fp32
+    for (int k = 0; k < kHalfbandOdd; ++k) g += 2.0 * (double)(float)odd[k] * std::cos((2 * k + 1) * theta);
     return g;
 }
 
@@ -151,7 +151,9 @@ static void design_interpolator(int log2u, std::vector<float>& coef) {
 }
 
 static int upload_constants(const gcwt_plan* p) {
-    GCWT_CUDA_OK(cudaMemcpyToSymbol(c_halfband, p->halfband_odd, sizeof(double) * kHalfbandOdd));
+    float hb[kHalfbandOdd];
+    for (int k = 0; k < kHalfbandOdd; ++k) hb[k] = (float)p->halfband_odd[k];
+    GCWT_CUDA_OK(cudaMemcpyToSymbol(c_halfband, hb, sizeof(float) * kHalfbandOdd));
     std::vector<float> all, part;
     for (int lu = 1; lu <= 3; ++lu) {
         design_interpolator(lu, part);
@@ -280,11 +282,13 @@ pyramid_kernel(const TIn* __restrict__ in, int64_t in_stride, int64_t in_lo, int
         const int64_t i = i0 + j;
         if (i - out_lo >= out_len) break;
         const int ctr = 2 * j + kHalfbandT;
-        double acc = 0.5 * (double)tile[ctr];
+        // fp32 accumulation, smallest taps first (fp64 would spend the kernel on conversions)
+        float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < kHalfbandOdd; ++k)
-            acc += c_halfband[k] * ((double)tile[ctr - (2 * k + 1)] + (double)tile[ctr + (2 * k + 1)]);
-        out[(int64_t)c * out_stride + (i - out_lo)] = (float)acc;
+        for (int k = kHalfbandOdd - 1; k >= 0; --k)
+            acc = fmaf(c_halfband[k], tile[ctr - (2 * k + 1)] + tile[ctr + (2 * k + 1)], acc);
+        acc = fmaf(0.5f, tile[ctr], acc);
+        out[(int64_t)c * out_stride + (i - out_lo)] = acc;
     }
 }
 
@@ -445,12 +449,14 @@ fused_banded_kernel(const FusedParams prm) {
     {
         const float* src = (const float*)prm.src + c * prm.src_stride - prm.src_lo;
         const int64_t i0 = t0 >> prm.log2d;                      // exact: t0 is a multiple of D
-        for (int i = tid; i < kChunkDec; i += 256) {
-            const int64_t u = i0 + i;
-            float v = 0.f;
-            if (u >= prm.src_lo && u < prm.src_hi) v = src[u];
-            ex[i] = make_float2(v, 0.f);
+        float raw[kChunkDec / 256];
+#pragma unroll
+        for (int k = 0; k < kChunkDec / 256; ++k) {
+            const int64_t u = i0 + tid + 256 * k;
+            raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
         }
+#pragma unroll
+        for (int k = 0; k < kChunkDec / 256; ++k) ex[tid + 256 * k] = make_float2(raw[k], 0.f);
         __syncthreads();
         float2* Y = smem_fft_forward<5>(ex, ex + kChunkDec, prm.twf);     // 1024 points
         // ---- (2) multiply by every scale's response (bins 0..255) ---------------
@@ -633,12 +639,14 @@ fused_interp_kernel(const FusedParams prm) {
     {   // (1) forward FFT of the decimated chunk, (2) multiply by every scale's response
         const float* src = (const float*)prm.src + c * prm.src_stride - prm.src_lo;
         const int64_t i0 = t0 >> prm.log2d;
-        for (int i = tid; i < kChunkDec; i += 256) {
-            const int64_t u = i0 + i;
-            float v = 0.f;
-            if (u >= prm.src_lo && u < prm.src_hi) v = src[u];
-            ex[i] = make_float2(v, 0.f);
+        float raw[kChunkDec / 256];
+#pragma unroll
+        for (int k = 0; k < kChunkDec / 256; ++k) {
+            const int64_t u = i0 + tid + 256 * k;
+            raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
         }
+#pragma unroll
+        for (int k = 0; k < kChunkDec / 256; ++k) ex[tid + 256 * k] = make_float2(raw[k], 0.f);
         __syncthreads();
         float2* Y = smem_fft_forward<5>(ex, ex + kChunkDec, prm.twf);
         const float2 y = Y[tid];
@@ -687,11 +695,14 @@ fused_interp_kernel(const FusedParams prm) {
 }
 
 // ---------------------------------------------------------------------------- full spectrum
-// smem: Yf[4096] | A[4096] | ex[4096]
-constexpr size_t kFullSmem = sizeof(float2) * 3 * 4096;
+// smem: Yf[4096] | ex[4096] | A[4096] | T[8*256] (next scale's table rows) | ids[64] | nmu[64]
+constexpr int kStageMu = 8;       // table rows of scales occupying <= 8 blocks are staged ahead
+constexpr size_t kFullSmem = sizeof(float2) * (3 * 4096 + kStageMu * 256) + sizeof(int) * 2 * kMaxFullScales;
 
 // radix-16 over the aliases m' + 256 mu of spectrum bin m' = tid, pruned to the first NMU
 // aliases (the others are empty for a filter that occupies only NMU blocks of 256 bins)
+// `tab` points at this thread's first table entry: in shared memory (staged by cp.async, stride
+// 256) for NMU <= kStageMu, in global memory otherwise.
 template <int NMU>
 __device__ __forceinline__ void full_prepass(const float2* __restrict__ Yf, const float2* __restrict__ tab,
                                              float2* __restrict__ A, const float2* tw4k) {
@@ -699,7 +710,7 @@ __device__ __forceinline__ void full_prepass(const float2* __restrict__ Yf, cons
     float2 a[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k)
-        a[k] = (k < NMU) ? cmul(Yf[tid + 256 * k], __ldg(tab + 256 * k)) : make_float2(0.f, 0.f);
+        a[k] = (k < NMU) ? cmul(Yf[tid + 256 * k], tab[256 * k]) : make_float2(0.f, 0.f);
     dft16<+1>(a);
 #pragma unroll
     for (int k = 0; k < 16; ++k) A[tid * 16 + (k ^ (tid & 15))] = k ? cmul(a[k], tw4k[k]) : a[k];
@@ -712,6 +723,9 @@ fused_full_kernel(const FusedParams prm) {
     float2* Yf = (float2*)smem_raw;      // order matters: the forward FFT's padded pass spills 2 KB into ex
     float2* ex = Yf + kFullN;
     float2* A = ex + kFullN;
+    float2* T = A + kFullN;              // T[tid + 256 k]: private to thread tid, filled by cp.async
+    int* s_ids = (int*)(T + kStageMu * 256);
+    int* s_nmu = s_ids + kMaxFullScales;
 
     const int tid = threadIdx.x;
     const int r = tid & 15;
@@ -723,12 +737,18 @@ fused_full_kernel(const FusedParams prm) {
     {
         const TIn* src = (const TIn*)prm.src + c * prm.src_stride;
         const double mu = prm.means[c];
-        for (int i = tid; i < kFullN; i += 256) {
-            const int64_t u = t0 + i;
-            float v = 0.f;
-            if (u >= prm.src_lo && u < prm.src_hi) v = (float)((double)src[u] - mu);
-            A[i] = make_float2(v, 0.f);
+        TIn raw[kFullN / 256];                                    // all 16 loads in flight at once
+        unsigned inside = 0;
+#pragma unroll
+        for (int k = 0; k < kFullN / 256; ++k) {
+            const int64_t u = t0 + tid + 256 * k;
+            const bool ok = u >= prm.src_lo && u < prm.src_hi;
+            raw[k] = ok ? src[u] : (TIn)0;
+            inside |= (unsigned)ok << k;
         }
+#pragma unroll
+        for (int k = 0; k < kFullN / 256; ++k)                    // zero padding outside the readable range
+            A[tid + 256 * k] = make_float2((inside >> k & 1) ? (float)((double)raw[k] - mu) : 0.f, 0.f);
         __syncthreads();
         smem_fft4096_forward(A, Yf, prm.twf);
     }
@@ -742,14 +762,32 @@ fused_full_kernel(const FusedParams prm) {
     const int rel = g * 16 + r;                                          // chunk-local sample of output k = 0
     const unsigned mask = valid_mask(rel, 8, (int)prm.offset, (int)min(prm.offset + prm.hop, prm.n - t0));
     OutT* const out_c = (OutT*)prm.out + c * prm.c_stride + t0;
+    if (tid < prm.n_scales) { s_ids[tid] = prm.scale_ids[tid]; s_nmu[tid] = prm.scale_nmu[tid]; }
+    __syncthreads();
+    // stage the table rows of scale `sn` (those this thread will read) into T
+    auto stage = [&](int sn) {
+        if (sn < prm.n_scales) {
+            const int nm = s_nmu[sn];
+            if (nm <= kStageMu) {
+                const float2* src = prm.table + (int64_t)sn * kFullN + tid;
+                for (int k = 0; k < nm; ++k) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(T + tid + 256 * k);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src + 256 * k) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0);
     for (int s = 0; s < prm.n_scales; ++s) {
         float2 a[16];
-        const float2* tab = prm.table + (int64_t)s * kFullN + tid;
-        const int nmu = prm.scale_nmu[s];
-        if (nmu == 2) full_prepass<2>(Yf, tab, A, tw4k);
-        else if (nmu == 4) full_prepass<4>(Yf, tab, A, tw4k);
-        else if (nmu == 8) full_prepass<8>(Yf, tab, A, tw4k);
-        else full_prepass<16>(Yf, tab, A, tw4k);
+        const int nmu = s_nmu[s];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (nmu == 2) full_prepass<2>(Yf, T + tid, A, tw4k);
+        else if (nmu == 4) full_prepass<4>(Yf, T + tid, A, tw4k);
+        else if (nmu == 8) full_prepass<8>(Yf, T + tid, A, tw4k);
+        else full_prepass<16>(Yf, prm.table + (int64_t)s * kFullN + tid, A, tw4k);
+        stage(s + 1);                                             // lands while this scale is transformed
         __syncthreads();
         // pass 1 of the 256-point transforms (16 columns)
 #pragma unroll
@@ -764,7 +802,7 @@ fused_full_kernel(const FusedParams prm) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
         dft16<+1>(a);
-        store_column<KIND>(out_c + (int64_t)prm.scale_ids[s] * prm.s_stride + rel, 256, mask, a);
+        store_column<KIND>(out_c + (int64_t)s_ids[s] * prm.s_stride + rel, 256, mask, a);
         // no trailing barrier: the next scale's pre-pass writes A, whose readers all passed
         // the second barrier above; its pass 1 writes ex only after the next first barrier,
         // which every thread reaches after finishing the reads of ex just done.
