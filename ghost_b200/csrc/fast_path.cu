@@ -316,6 +316,18 @@ struct FusedParams {
     const int32_t* scale_nmu; // full: occupied 256-bin blocks per scale
 };
 
+// e^{+2 pi i k / 4096} from the table of e^{-2 pi i k / 4096}
+__device__ __forceinline__ float2 tw_pos(const float2* __restrict__ twf, int k) {
+    const float2 t = __ldg(twf + (k & (kFullN - 1)));
+    return make_float2(t.x, -t.y);
+}
+
+__device__ __forceinline__ float sqrt_abs_approx(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fabsf(v)));  // |v| folds into the MUFU operand
+    return r;
+}
+
 __device__ __forceinline__ float sqrt_approx(float v) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));       // one MUFU op, rel. error 2^-23
@@ -467,10 +479,13 @@ fused_banded_kernel(const FusedParams prm) {
     // per-thread constants
     float2 tw[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) tw[k] = expipi((float)(2 * g * k) * (1.0f / 256.0f));
+    for (int k = 0; k < 16; ++k) tw[k] = tw_pos(prm.twf, 16 * g * k);      // e^{2 pi i g k / 256}
     const int col0 = unit * prm.iters * 16;
     float2 R[16];
-    {
+    if (prm.p_cols == 16) {                                      // 4096-point chunk: phases are table entries
+#pragma unroll
+        for (int i = 0; i < 16; ++i) R[i] = tw_pos(prm.twf, (g + 16 * i) * (col0 + r));
+    } else {
         const int64_t n2 = col0 + r;
         const int64_t mask = ((int64_t)prm.p_cols * kBins) - 1;  // nc_full - 1 (power of two)
 #pragma unroll
@@ -551,7 +566,8 @@ __device__ __forceinline__ void interp_rows(const float* __restrict__ pc, float*
 #pragma unroll
         for (int j = 0; j < kInterpT - 1; ++j) w[j] = pc[a - (kInterpT / 2 - 1) + j];
         float* op = row + ((int64_t)a << lu) + phi;
-        for (int base = a; base < b_t; base += kInterpT) {
+        int base = a;
+        for (; base + kInterpT <= b_t; base += kInterpT) {        // full groups: no predicates
 #pragma unroll
             for (int u = 0; u < kInterpT; ++u) {
                 // window of iota = base + u is pc[iota-4 .. iota+5], kept in w[(u + j) % T]
@@ -559,10 +575,20 @@ __device__ __forceinline__ void interp_rows(const float* __restrict__ pc, float*
                 float acc = c[0] * w[u % kInterpT];
 #pragma unroll
                 for (int j = 1; j < kInterpT; ++j) acc = fmaf(c[j], w[(u + j) % kInterpT], acc);
-                acc = fmaxf(acc, 0.f);
-                if (KIND == GCWT_OUT_AMPLITUDE) acc = sqrt_approx(acc);
-                st_pred(op, acc, (unsigned)(base + u < b_t));
-                op += U;
+                // interpolated power can undershoot zero by rounding-size amounts near nulls
+                op[(int64_t)u << lu] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_abs_approx(acc) : fmaxf(acc, 0.f);
+            }
+            op += (int64_t)kInterpT << lu;
+        }
+        if (base < b_t) {                                         // tail group
+#pragma unroll
+            for (int u = 0; u < kInterpT; ++u) {
+                w[(u + kInterpT - 1) % kInterpT] = pc[base + u + kInterpT / 2];
+                float acc = c[0] * w[u % kInterpT];
+#pragma unroll
+                for (int j = 1; j < kInterpT; ++j) acc = fmaf(c[j], w[(u + j) % kInterpT], acc);
+                acc = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_abs_approx(acc) : fmaxf(acc, 0.f);
+                st_pred(op + ((int64_t)u << lu), acc, (unsigned)(base + u < b_t));
             }
         }
     }
@@ -587,12 +613,9 @@ __device__ __forceinline__ void interp_rows_small(const float* __restrict__ pc, 
             float acc = c_interp_small[COFF + phi * kInterpT] * w[0];
 #pragma unroll
             for (int j = 1; j < kInterpT; ++j) acc = fmaf(c_interp_small[COFF + phi * kInterpT + j], w[j], acc);
-            o[phi] = fmaxf(acc, 0.f);
+            o[phi] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_abs_approx(acc) : fmaxf(acc, 0.f);
         }
-        if (KIND == GCWT_OUT_AMPLITUDE) {
-#pragma unroll
-            for (int phi = 0; phi < U; ++phi) o[phi] = sqrt_approx(o[phi]);
-        }
+        if (KIND == GCWT_OUT_AMPLITUDE) o[0] = sqrt_approx(o[0]);
         float* op = row + (int64_t)iota * U;
         if ((iota + 1) * U <= own_hi) {
             if (U == 2) *(float2*)op = make_float2(o[0], o[1]);
@@ -655,8 +678,8 @@ fused_interp_kernel(const FusedParams prm) {
     float2 tw[16], R[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        tw[k] = expipi((float)(2 * g * k) * (1.0f / 256.0f));
-        R[k] = expipi((float)((2 * (g + 16 * k) * col) & 4095) * (1.0f / 2048.0f));   // e^{2 pi i m col / 2048}
+        tw[k] = tw_pos(prm.twf, 16 * g * k);                      // e^{2 pi i g k / 256}
+        R[k] = tw_pos(prm.twf, 2 * (g + 16 * k) * col);           // e^{2 pi i m col / 2048}
     }
     __syncthreads();
 
@@ -755,8 +778,8 @@ fused_full_kernel(const FusedParams prm) {
     float2 tw[16], tw4k[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        tw[k] = expipi((float)(2 * g * k) * (1.0f / 256.0f));
-        tw4k[k] = expipi((float)(2 * tid * k) * (1.0f / 4096.0f));
+        tw[k] = tw_pos(prm.twf, 16 * g * k);                      // e^{2 pi i g k / 256}
+        tw4k[k] = tw_pos(prm.twf, tid * k);                       // e^{2 pi i m' k / 4096}
     }
     typedef typename out_elem<KIND>::type OutT;
     const int rel = g * 16 + r;                                          // chunk-local sample of output k = 0

@@ -179,6 +179,24 @@ def test_fp32_gamma_beta_grid(gamma, beta, vpo):
     assert err.max() <= FP32_BAR, (gamma, beta, int(np.argmax(err)), err.max(), cwt.last_plan.levels().tolist())
 
 
+def test_fp32_long_kernels_high_levels():
+    """Config 3/4 territory: 30 kHz, kernels of 4 k ... 236 k taps (decimation levels 5 ... 11,
+    coarse spacings up to 1024) against the oracle, at hand-picked frequencies."""
+    fs, n = 30000.0, 1500000
+    x = synth.chirp_pink(n, fs, 21, np.float32)
+    freqs = np.array([120.0, 61.0, 30.0, 13.0, 7.0, 4.0, 2.5, 1.7673])
+    W, _, L = orc.cwt_complex(x, fs, frequencies=freqs, parallel=True)
+    assert int(L.max()) == 236760 or int(L.max()) > 230000
+    xd = torch.from_numpy(x[None, :]).cuda()
+    for output, want in (("amplitude", np.abs(W)), ("power", np.abs(W) ** 2), ("complex", W)):
+        plan, _ = _plan_for(3, 20, fs, freqs, dtype=np.float32, output=output)
+        lev = plan.levels()
+        assert lev.min() >= 5 and lev.max() >= 11
+        got = plan.execute(xd)[0].cpu().numpy()
+        err = _l2rel(got.astype(want.dtype), want)
+        assert err.max() <= FP32_BAR, (output, err)
+
+
 def test_fp32_generic_fallback_matches():
     fs, n = 1000.0, 30000
     x = synth.chirp_pink(n, fs, 2, np.float32)
