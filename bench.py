@@ -35,8 +35,10 @@ WORKLOADS = {
                  desc="64ch x 1.25kHz x 30min, 96 scales, fp32 amplitude"),
     "cfg1": dict(fs=1000.0, n=60000, channels=1, freq_limits=None, vpo=10, output="amplitude",
                  desc="1ch x 1kHz x 60s, 84 scales, fp32 amplitude"),
-    "cfg3slice": dict(fs=30000.0, n=18000000, channels=2, freq_limits=[1.7, 15000.0], vpo=10, output="power",
-                      desc="2ch of cfg3 (30kHz x 10min, 128 scales, fp32 power)"),
+    # config 3 of BASELINE.json is 256 channels over 8 GPUs = 32 channels per GPU; its result (295 GB
+    # per GPU) exceeds HBM, so it is produced in time tiles into a reused buffer (tile = samples per tile)
+    "cfg3": dict(fs=30000.0, n=18000000, channels=32, freq_limits=[1.7, 15000.0], vpo=10, output="power",
+                 tile=2250000, desc="32ch/GPU x 30kHz x 10min, 128 scales, fp32 power, streamed in 8 time tiles"),
 }
 
 
@@ -47,6 +49,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=None, help="override samples per channel")
     ap.add_argument("--channels", type=int, default=None, help="channels per GPU (default: workload's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -183,6 +186,8 @@ def run_ours(args):
     wl = dict(WORKLOADS[args.workload])
     if args.channels:
         wl["channels"] = args.channels
+    if args.samples:
+        wl["n"] = args.samples
     fs, n, nch = wl["fs"], wl["n"], wl["channels"]
     freqs = plan_frequencies(wl)
     m = Morse(fs=fs)
@@ -201,8 +206,16 @@ def run_ours(args):
         if c >= len(base):
             x_host[c] = torch.roll(x_host[c], 1009 * c)
     x_dev = x_host.to(dev, non_blocking=True)
-    out = plan.alloc_out(nch, n)
+    tile = int(wl.get("tile", 0))
+    out = plan.alloc_out(nch, tile if tile else n)
+    step_means = plan.channel_means(x_dev) if tile else None
     torch.cuda.synchronize(dev)
+
+    def one_pass():
+        if tile:
+            plan.execute_tiled(x_dev, tile, out=out, means=step_means)
+        else:
+            plan.execute(x_dev, out)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -212,7 +225,7 @@ def run_ours(args):
 
     # ---- device-resident timing --------------------------------------------------
     for _ in range(args.warmup):
-        plan.execute(x_dev, out)
+        one_pass()
     barrier()
     plan.profile(True)
     plan.profile_read(reset=True)
@@ -224,7 +237,7 @@ def run_ours(args):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        plan.execute(x_dev, out)
+        one_pass()
     ev1.record()
     barrier()
     sampler.stop_flag = True
@@ -284,7 +297,7 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer path ----------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not tile:
         e2e = run_e2e(args, plan, x_host, dev, world, nch, n, S, out_el)
 
     # ---- CPU baseline (rank 0, N = 1) ------------------------------------------------------

@@ -144,6 +144,32 @@ class CwtPlan:
             out.data_ptr() + out_start * osz, out.stride(1), out.stride(0), st))
         return out
 
+    def execute_tiled(self, x, tile, out=None, consumer=None, means=None):
+        """Transform a recording whose result does not fit in device memory.
+
+        The samples are cut into tiles of ``tile`` samples; each tile is transformed with
+        real-sample halos on both sides (exact: the filters are FIR) into
+        the same reused ``out`` buffer (C, S, tile) and handed to ``consumer(out, start,
+        stop)`` -- which must be done with the buffer when it returns (same stream).
+        Returns the number of coefficients produced."""
+        torch = _torch()
+        n_ch, n = x.shape
+        tile = int(min(tile, n))
+        if out is None:
+            out = self.alloc_out(n_ch, tile)
+        if means is None:
+            means = self.channel_means(x)
+        halo = self.max_length - 1
+        done = 0
+        for a in range(0, n, tile):
+            b = min(n, a + tile)
+            self.execute(x, out, means=means, start=a, stop=b, halo_left=min(halo, a),
+                         halo_right=min(halo, n - b), out_start=0)
+            if consumer is not None:
+                consumer(out, a, b)
+            done += (b - a) * n_ch * self.n_scales
+        return done
+
     def execute_host(self, x, out=None, means=None):
         """Host-buffer entry point (numpy in, numpy out) through gcwt_execute_host."""
         x = np.ascontiguousarray(x)
