@@ -288,10 +288,17 @@ def run_ours(args):
             "share_of_step": (fams[dom]["ms_per_step"] / ms_step) if dom else None,
             "families": fams, "mean_pyramid_ms_per_step": prof["mean+pyramid"][0] / args.steps,
             "whole_step": {"achieved": whole_gbs, "frac": whole_gbs / peak}}
+    # measured DRAM traffic (dram__bytes_read + dram__bytes_write of one ncu --set full capture of this
+    # kernel family, profiles/traffic.json) scaled from the captured channel count to this run's
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file) and dom:
         try:
-            roof["traffic"] = json.load(open(traffic_file)).get(dom + "_bytes_per_launch")
+            tj = json.load(open(traffic_file))
+            ratio = tj.get(dom + "_traffic_over_algorithmic")
+            if ratio is not None:
+                roof["traffic"] = ratio * fams[dom]["bytes_per_step"]
+                roof["traffic_note"] = "per step over all %s launches; ncu ratio traffic/algorithmic = %.3f (%s)" % (
+                    dom, ratio, tj.get("source", ""))
         except Exception:
             pass
 
