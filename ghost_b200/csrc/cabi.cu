@@ -139,13 +139,19 @@ int gcwt_plan_create(gcwt_plan** out, const gcwt_plan_desc* d) {
     p->terms.assign(d->terms, d->terms + off);
 
     int rc = GCWT_OK;
-    if (p->compute_type == GCWT_F32) rc = fast_plan_build(p);
-    else for (int s = 0; s < p->n_scales; ++s) p->generic_ids.push_back(s);
-    if (rc == GCWT_OK) {
+    {
         cudaError_t e = cudaMalloc((void**)&p->d_scales, sizeof(ScaleInfo) * p->n_scales);
         if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_terms, sizeof(double) * p->terms.size());
         if (e == cudaSuccess) e = cudaMemcpy(p->d_scales, p->scales.data(), sizeof(ScaleInfo) * p->n_scales, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(p->d_terms, p->terms.data(), sizeof(double) * p->terms.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error(std::string("plan_create: ") + cudaGetErrorString(e)); rc = GCWT_ERR_CUDA; }
+    }
+    if (rc == GCWT_OK) {
+        if (p->compute_type == GCWT_F32) rc = fast_plan_build(p);
+        else for (int s = 0; s < p->n_scales; ++s) p->generic_ids.push_back(s);
+    }
+    if (rc == GCWT_OK && p->compute_type == GCWT_F32) {      // levels were chosen by the planner: refresh the device copy
+        cudaError_t e = cudaMemcpy(p->d_scales, p->scales.data(), sizeof(ScaleInfo) * p->n_scales, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { set_error(std::string("plan_create: ") + cudaGetErrorString(e)); rc = GCWT_ERR_CUDA; }
     }
     if (rc != GCWT_OK) { gcwt_plan_destroy(p); return rc; }

@@ -71,49 +71,82 @@ static double halfband_gain(const double* odd, double theta) {
     return g;
 }
 
-// out-of-band energy test of one scale on the (1024 << level)-point grid
-static bool band_fits(const gcwt_plan* p, const ScaleInfo& sc, int level, double* g_out /*kBins or null*/) {
-    const int64_t nc = (int64_t)kChunkDec << level;
+// ---- plan-time evaluation of the exact responses, on the device ------------------------------
+// Per scale: kBins values on each candidate grid 1024 << level (level = kMinFastLevel ...
+// kMaxFastLevel) followed by kFullN values on the 4096-point grid.
+constexpr int kPlanLevels = kMaxFastLevel - kMinFastLevel + 1;
+constexpr int kPlanRow = kPlanLevels * kBins + kFullN;
+
+__global__ void plan_response_kernel(const ScaleInfo* __restrict__ scales, const double* __restrict__ terms,
+                                     double* __restrict__ out) {
+    const int s = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kPlanRow) return;
+    const ScaleInfo sc = scales[s];
+    int64_t n, m;
+    if (i < kPlanLevels * kBins) { n = (int64_t)kChunkDec << (kMinFastLevel + i / kBins); m = i % kBins; }
+    else { n = kFullN; m = i - kPlanLevels * kBins; }
+    out[(int64_t)s * kPlanRow + i] = morse_response(m, n, sc.L, sc.k_first, sc.n_terms, terms + sc.term_off);
+}
+
+struct PlanResponses {
+    std::vector<double> g;                      // [n_scales][kPlanRow]
+    const double* level(int s, int lev) const { return g.data() + (size_t)s * kPlanRow + (size_t)(lev - kMinFastLevel) * kBins; }
+    const double* full(int s) const { return g.data() + (size_t)s * kPlanRow + (size_t)kPlanLevels * kBins; }
+};
+
+static int compute_plan_responses(const gcwt_plan* p, PlanResponses& pr) {
+    const size_t count = (size_t)p->n_scales * kPlanRow;
+    double* d = nullptr;
+    GCWT_CUDA_OK(cudaMalloc((void**)&d, sizeof(double) * count));
+    plan_response_kernel<<<dim3((kPlanRow + 127) / 128, p->n_scales), 128>>>(p->d_scales, p->d_terms, d);
+    count_launch();
+    pr.g.resize(count);
+    cudaError_t e = cudaMemcpy(pr.g.data(), d, sizeof(double) * count, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error(std::string("plan responses: ") + cudaGetErrorString(e)); return GCWT_ERR_CUDA; }
+    return GCWT_OK;
+}
+
+static double filter_energy(const gcwt_plan* p, const ScaleInfo& sc, int64_t n) {
     const double* X = p->terms.data() + sc.term_off;
+    double e = 0.0;
+    for (int t = 0; t < sc.n_terms; ++t) e += X[t] * X[t];
+    return e * (double)n / (double)sc.L;        // Parseval: sum_j |H(w_j)|^2 over an n-point grid, n >= L
+}
+
+// out-of-band energy test of one scale on the (1024 << level)-point grid
+static bool band_fits(const gcwt_plan* p, const PlanResponses& pr, int s, int level) {
+    const double* g = pr.level(s, level);
     double e_in = 0.0;
-    for (int m = 0; m < kBins; ++m) {
-        const double g = morse_response(m, nc, sc.L, sc.k_first, sc.n_terms, X);
-        if (g_out) g_out[m] = g;
-        e_in += g * g;
-    }
-    double e_tot = 0.0;
-    for (int t = 0; t < sc.n_terms; ++t) e_tot += X[t] * X[t];
-    e_tot *= (double)nc / (double)sc.L;
+    for (int m = 0; m < kBins; ++m) e_in += g[m] * g[m];
+    const double e_tot = filter_energy(p, p->scales[s], (int64_t)kChunkDec << level);
     return (1.0 - e_in / e_tot) < p->band_tol * p->band_tol;
 }
 
 // Full-spectrum kernel: how many 256-bin blocks of the 4096-point grid does the filter occupy?
 // One-sided filters leave the upper blocks empty (below band_tol in energy), and the kernel's
 // radix-16 pre-pass over the 16 aliases of a bin is pruned accordingly.
-static int full_extent(const gcwt_plan* p, const ScaleInfo& sc) {
-    const double* X = p->terms.data() + sc.term_off;
-    double e_tot = 0.0;
-    for (int t = 0; t < sc.n_terms; ++t) e_tot += X[t] * X[t];
-    e_tot *= (double)kFullN / (double)sc.L;
+static int full_extent(const gcwt_plan* p, const PlanResponses& pr, int s) {
+    const double* g = pr.full(s);
+    const double e_tot = filter_energy(p, p->scales[s], kFullN);
     double e_in = 0.0;
     int m = 0;
     for (int nmu = 2; nmu <= 8; nmu *= 2) {
-        for (; m < nmu * kBins; ++m) {
-            const double g = morse_response(m, kFullN, sc.L, sc.k_first, sc.n_terms, X);
-            e_in += g * g;
-        }
+        for (; m < nmu * kBins; ++m) e_in += g[m] * g[m];
         if ((1.0 - e_in / e_tot) < p->band_tol * p->band_tol) return nmu;
     }
     return 16;
 }
 
-static int choose_level(const gcwt_plan* p, const ScaleInfo& sc) {
+static int choose_level(const gcwt_plan* p, const PlanResponses& pr, int s) {
+    const ScaleInfo& sc = p->scales[s];
     if (!(p->flags & GCWT_FLAG_FORCE_GENERIC)) {
         int lo = kMinFastLevel;
         while (lo <= kMaxFastLevel && (double)(sc.L - 1) > kMaxHaloFrac * (double)((int64_t)kChunkDec << lo)) ++lo;
         int hi = std::min(kMaxFastLevel, ilog2_ceil(sc.L) + 1);
         for (int lev = hi; lev >= lo; --lev)
-            if (band_fits(p, sc, lev, nullptr)) return lev;
+            if (band_fits(p, pr, s, lev)) return lev;
         if ((double)(sc.L - 1) <= kMaxHaloFrac * kFullN) return -1;
     }
     return -2;
@@ -175,11 +208,19 @@ int fast_plan_build(gcwt_plan* p) {
         GCWT_CUDA_OK(cudaMalloc((void**)&p->d_twiddle, sizeof(float2) * kFullN));
         GCWT_CUDA_OK(cudaMemcpy(p->d_twiddle, tw.data(), sizeof(float2) * kFullN, cudaMemcpyHostToDevice));
     }
+    PlanResponses pr;
+    { int rc = compute_plan_responses(p, pr); if (rc) return rc; }
+    // half-band gains at theta = 2 pi m / (1024 * 2^j), j = 1 .. kMaxFastLevel: the decimator
+    // response of a level is the product over its stages
+    std::vector<double> hb((size_t)(kMaxFastLevel + 1) * kBins, 1.0);
+    for (int j = 1; j <= kMaxFastLevel; ++j)
+        for (int m = 0; m < kBins; ++m)
+            hb[(size_t)j * kBins + m] = halfband_gain(p->halfband_odd, 2.0 * M_PI * (double)m / (double)((int64_t)kChunkDec << j));
     std::map<int, std::vector<int>> by_level;
     p->max_level = 0;
     for (int s = 0; s < p->n_scales; ++s) {
         ScaleInfo& sc = p->scales[s];
-        sc.level = choose_level(p, sc);
+        sc.level = choose_level(p, pr, s);
         if (sc.level == -2) p->generic_ids.push_back(s);
         else by_level[sc.level].push_back(s);
         p->max_level = std::max(p->max_level, sc.level);
@@ -205,12 +246,11 @@ int fast_plan_build(gcwt_plan* p) {
             std::vector<float2> tab((size_t)ns * nb);
             for (int i = 0; i < ns; ++i) {
                 const ScaleInfo& sc = p->scales[fc.scale_ids[i]];
-                const double* X = p->terms.data() + sc.term_off;
+                const double* gsrc = level >= 0 ? pr.level(fc.scale_ids[i], level) : pr.full(fc.scale_ids[i]);
                 for (int m = 0; m < nb; ++m) {
-                    double g = morse_response(m, fc.nc_full, sc.L, sc.k_first, sc.n_terms, X);
+                    double g = gsrc[m];
                     if (level >= 0) {
-                        const double w = 2.0 * M_PI * (double)m / (double)fc.nc_full;
-                        for (int st = 0; st < level; ++st) g /= halfband_gain(p->halfband_odd, w * (double)(1 << st));
+                        for (int j = 1; j <= level; ++j) g /= hb[(size_t)j * kBins + m];
                         g /= (double)kChunkDec;
                     } else {
                         g /= (double)kFullN;
@@ -233,7 +273,7 @@ int fast_plan_build(gcwt_plan* p) {
                 GCWT_CUDA_OK(cudaMemcpy(fc.d_coef, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
             }
             if (level < 0) {
-                for (int id : fc.scale_ids) fc.scale_nmu.push_back(full_extent(p, p->scales[id]));
+                for (int id : fc.scale_ids) fc.scale_nmu.push_back(full_extent(p, pr, id));
                 GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_scale_nmu, sizeof(int32_t) * ns));
                 GCWT_CUDA_OK(cudaMemcpy(fc.d_scale_nmu, fc.scale_nmu.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
             }
