@@ -8,7 +8,8 @@ fallback.
 from . import utils
 from . import formats
 from . import wave
+from . import sigtools
 from .wave import ContinuousWaveletTransform, Morse
 
 __version__ = "0.1.0"
-__all__ = ["ContinuousWaveletTransform", "Morse", "wave", "formats", "utils"]
+__all__ = ["ContinuousWaveletTransform", "Morse", "wave", "sigtools", "formats", "utils"]

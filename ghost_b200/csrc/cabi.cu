@@ -68,6 +68,11 @@ int filter_response_device(int64_t L, int k_first, int n_terms, const double* te
 
 int morse_kernel_device(int64_t L, int k_first, int n_terms, const double* terms_host, double* out_host);
 
+int sig_dft_host(const double* x_host, int64_t n, int sign, double* out_host);
+int sig_analytic_host(const double* x_host, int64_t n, double* out_host);
+int sig_fastconv_host(const double* sig_host, int sig_complex, int64_t n, const double* ker_host, int ker_complex,
+                      int64_t m, double* out_host);
+
 static int check_exec_args(const gcwt_plan* plan, const void* x, int in_type, int64_t n_channels,
                            int64_t n_samples, int64_t x_stride, const void* out) {
     if (!plan) { set_error("plan is NULL"); return GCWT_ERR_ARG; }
@@ -309,6 +314,25 @@ int gcwt_morse_kernel(int64_t length, int32_t k_first, int32_t n_terms, const do
     }
     GCWT_CUDA_OK(cudaSetDevice(device));
     return morse_kernel_device(length, k_first, n_terms, terms, out_host);
+}
+
+int gcwt_fastconv(const double* signal, int32_t signal_is_complex, int64_t n, const double* kernel,
+                  int32_t kernel_is_complex, int64_t m, double* out_full, int32_t device) {
+    if (!signal || !kernel || !out_full || n < 1 || m < 1) { set_error("fastconv: bad argument"); return GCWT_ERR_ARG; }
+    GCWT_CUDA_OK(cudaSetDevice(device));
+    return sig_fastconv_host(signal, signal_is_complex, n, kernel, kernel_is_complex, m, out_full);
+}
+
+int gcwt_dft(const double* x_complex, int64_t n, int32_t sign, double* out_complex, int32_t device) {
+    if (!x_complex || !out_complex || n < 1 || (sign != 1 && sign != -1)) { set_error("dft: bad argument"); return GCWT_ERR_ARG; }
+    GCWT_CUDA_OK(cudaSetDevice(device));
+    return sig_dft_host(x_complex, n, sign, out_complex);
+}
+
+int gcwt_analytic_signal(const double* x, int64_t n, double* out_complex, int32_t device) {
+    if (!x || !out_complex || n < 1) { set_error("analytic_signal: bad argument"); return GCWT_ERR_ARG; }
+    GCWT_CUDA_OK(cudaSetDevice(device));
+    return sig_analytic_host(x, n, out_complex);
 }
 
 }  // extern "C"

@@ -131,6 +131,21 @@ int gcwt_filter_response(int64_t length, int32_t k_first, int32_t n_terms,
 int gcwt_morse_kernel(int64_t length, int32_t k_first, int32_t n_terms, const double *terms,
                       double *out_host, int32_t device);
 
+/* ---- sigtools helpers; host pointers, complex128 like the reference ----
+ *
+ * gcwt_fastconv: full linear convolution, n + m - 1 complex outputs (interleaved re, im).  Replaces
+ *   fastconv_scipy / fastconv_fftw (ghost/sigtools/convolution.py:16-216); the 'same' / 'valid'
+ *   slices (convolution.py:79-87) are views of this result.  *_is_complex: 0 = real doubles.
+ * gcwt_dft: DFT of any length (Bluestein chirp-z for non powers of two), sign -1 forward, +1
+ *   backward (unscaled).  Replaces chirpz_dft (ghost/sigtools/fourier.py:9-48).
+ * gcwt_analytic_signal: x + i Hilbert(x) for a real signal of any length.  Replaces
+ *   analytic_signal_scipy / analytic_signal_fftw (ghost/sigtools/analytic.py:15-112). */
+int gcwt_fastconv(const double *signal, int32_t signal_is_complex, int64_t n,
+                  const double *kernel, int32_t kernel_is_complex, int64_t m,
+                  double *out_full, int32_t device);
+int gcwt_dft(const double *x_complex, int64_t n, int32_t sign, double *out_complex, int32_t device);
+int gcwt_analytic_signal(const double *x, int64_t n, double *out_complex, int32_t device);
+
 /* Bytes of device workspace the plan currently holds (grows on demand in execute). */
 size_t gcwt_plan_workspace_bytes(const gcwt_plan *plan);
 
