@@ -410,33 +410,36 @@ __device__ __forceinline__ unsigned valid_mask(int rel, int sh, int lo, int hi) 
     return k_hi > k_lo ? (((1u << k_hi) - 1u) & ~((1u << k_lo) - 1u)) : 0u;
 }
 
-// Radix-4 Stockham FFT in shared memory, forward sign, N = 4^PASSES <= 1024 points, 256
-// threads, twiddles from the 4096-entry table `tw`.  Result lands in `a` when PASSES is even,
-// in `b` when odd.
-template <int PASSES>
-__device__ __forceinline__ float2* smem_fft_forward(float2* a, float2* b, const float2* __restrict__ tw) {
-    constexpr int N = 1 << (2 * PASSES);
-    constexpr int M = N / 4;
-    int ns = 1;
-#pragma unroll 1
-    for (int pass = 0; pass < PASSES; ++pass) {
-        const int tstep = (kFullN / 4) / ns;                 // table stride of e^{-2 pi i / (4 ns)}
-        for (int j = threadIdx.x; j < M; j += 256) {
-            const int k = j & (ns - 1);
-            float2 v0 = a[j], v1 = a[j + M], v2 = a[j + 2 * M], v3 = a[j + 3 * M];
-            if (ns > 1) {
-                const int idx = k * tstep;
-                v1 = cmul(v1, __ldg(tw + idx));
-                v2 = cmul(v2, __ldg(tw + 2 * idx));
-                v3 = cmul(v3, __ldg(tw + 3 * idx));
-            }
-            dft4<-1>(v0, v1, v2, v3);
-            const int j0 = ((j - k) << 2) + k;
-            b[j0] = v0; b[j0 + ns] = v1; b[j0 + 2 * ns] = v2; b[j0 + 3 * ns] = v3;
+// 1024-point forward FFT: five radix-4 Stockham passes, 256 threads, one butterfly per thread and
+// pass.  Thread j handles butterfly j in every pass, so all of its 12 twiddles are fetched up
+// front in one batch of independent loads (one memory latency instead of four in a chain).
+// Input in `a`, scratch `b`; returns the buffer that holds the result.
+__device__ __forceinline__ float2* smem_fft1024_forward(float2* a, float2* b, const float2* __restrict__ tw) {
+    constexpr int M = 256;
+    const int j = threadIdx.x;
+    float2 w[4][3];
+#pragma unroll
+    for (int p = 1; p < 5; ++p) {
+        const int ns = 1 << (2 * p);
+        const int idx = (j & (ns - 1)) * ((kFullN / 4) / ns);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) w[p - 1][r] = __ldg(tw + (r + 1) * idx);
+    }
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+        const int ns = 1 << (2 * p);
+        const int k = j & (ns - 1);
+        float2 v0 = a[j], v1 = a[j + M], v2 = a[j + 2 * M], v3 = a[j + 3 * M];
+        if (p > 0) {
+            v1 = cmul(v1, w[p - 1][0]);
+            v2 = cmul(v2, w[p - 1][1]);
+            v3 = cmul(v3, w[p - 1][2]);
         }
+        dft4<-1>(v0, v1, v2, v3);
+        const int j0 = ((j - k) << 2) + k;
+        b[j0] = v0; b[j0 + ns] = v1; b[j0 + 2 * ns] = v2; b[j0 + 3 * ns] = v3;
         __syncthreads();
         float2* t = a; a = b; b = t;
-        ns <<= 2;
     }
     return a;
 }
@@ -446,7 +449,12 @@ __device__ __forceinline__ float2* smem_fft_forward(float2* a, float2* b, const 
 // pass writes with a pad of one element per 16 to stay free of bank conflicts).
 __device__ __forceinline__ void smem_fft4096_forward(float2* x, float2* y, const float2* __restrict__ tw) {
     const int tid = threadIdx.x;
-    float2 v[16];
+    float2 v[16], w2[16], w3[16];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) {                                 // both passes' twiddles, one batch of loads
+        w2[r] = __ldg(tw + r * (tid & 15) * 16);
+        w3[r] = __ldg(tw + r * tid);
+    }
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = x[tid + 256 * r];
     dft16<-1>(v);
@@ -458,7 +466,7 @@ __device__ __forceinline__ void smem_fft4096_forward(float2* x, float2* y, const
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = y[tid + 256 * r + (tid >> 4) + 16 * r];
 #pragma unroll
-        for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(tw + r * k * 16));
+        for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], w2[r]);
         dft16<-1>(v);
         const int j0 = ((tid - k) << 4) + k;
 #pragma unroll
@@ -468,7 +476,7 @@ __device__ __forceinline__ void smem_fft4096_forward(float2* x, float2* y, const
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = x[tid + 256 * r];
 #pragma unroll
-    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(tw + r * tid));
+    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], w3[r]);
     dft16<-1>(v);
 #pragma unroll
     for (int r = 0; r < 16; ++r) y[tid + 256 * r] = v[r];
@@ -477,7 +485,7 @@ __device__ __forceinline__ void smem_fft4096_forward(float2* x, float2* y, const
 
 // ---------------------------------------------------------------------------- banded
 // smem: ex[2][4096] | Zs[kMaxClassScales][256] | Estep[256]
-constexpr size_t kBandedSmem = sizeof(float2) * (2 * 4096 + kMaxClassScales * kBins + kBins);
+constexpr size_t kBandedSmem = sizeof(float2) * (2 * 4096 + kMaxClassScales * kBins + kBins) + sizeof(int) * kMaxClassScales;
 
 template <int KIND>
 __global__ void __launch_bounds__(256, 2)
@@ -486,8 +494,10 @@ fused_banded_kernel(const FusedParams prm) {
     float2* ex = (float2*)smem_raw;
     float2* Zs = ex + 2 * 4096;
     float2* Estep = Zs + kMaxClassScales * kBins;
+    int* s_ids = (int*)(Estep + kBins);
 
     const int tid = threadIdx.x;
+    if (tid < prm.n_scales) s_ids[tid] = prm.scale_ids[tid];
     const int r = tid & 15;            // column within the block of 16
     const int g = tid >> 4;            // m_lo in pass 1, n_lo in pass 2
 
@@ -510,7 +520,7 @@ fused_banded_kernel(const FusedParams prm) {
 #pragma unroll
         for (int k = 0; k < kChunkDec / 256; ++k) ex[tid + 256 * k] = make_float2(raw[k], 0.f);
         __syncthreads();
-        float2* Y = smem_fft_forward<5>(ex, ex + kChunkDec, prm.twf);     // 1024 points
+        float2* Y = smem_fft1024_forward(ex, ex + kChunkDec, prm.twf);
         // ---- (2) multiply by every scale's response (bins 0..255) ---------------
         const float2 y = Y[tid];
         for (int s = 0; s < prm.n_scales; ++s) Zs[s * kBins + tid] = cmul(y, prm.table[s * kBins + tid]);
@@ -562,7 +572,7 @@ fused_banded_kernel(const FusedParams prm) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
             dft16<+1>(a);
-            store_column<KIND>(out_c + (int64_t)prm.scale_ids[s] * prm.s_stride + rel, kstride, mask, a);
+            store_column<KIND>(out_c + (int64_t)s_ids[s] * prm.s_stride + rel, kstride, mask, a);
             buf ^= 1;
         }
 #pragma unroll
@@ -578,12 +588,12 @@ fused_banded_kernel(const FusedParams prm) {
 // moves these classes from the FP32-issue bound to the HBM bound.
 // smem: ex[4096] float2 | Zs[kMaxClassScales][256] float2 | Pc[2][kPcStride] float
 constexpr int kPcStride = kCoarse + 16;           // % 32 == 16: the two scales of a pair hit different banks
-constexpr size_t kInterpSmem = sizeof(float2) * (4096 + kMaxClassScales * kBins) + sizeof(float) * 2 * kPcStride;
+constexpr size_t kInterpSmem = sizeof(float2) * (4096 + kMaxClassScales * kBins) + sizeof(float) * 2 * kPcStride + sizeof(int) * kMaxClassScales;
 
 template <int KIND>
 __device__ __forceinline__ void interp_rows(const float* __restrict__ pc, float* __restrict__ row,
-                                            const float* __restrict__ coef, int lu, int ia, int ib,
-                                            int own_hi) {
+                                            const float* __restrict__ coef, const float* c0, int lu,
+                                            int ia, int ib, int own_hi) {
     // thread <-> phase phi; lanes of a warp hold consecutive phases of the same coarse interval,
     // so the window loads are shared-memory broadcasts and the stores are contiguous.
     const int U = 1 << lu;
@@ -600,7 +610,7 @@ __device__ __forceinline__ void interp_rows(const float* __restrict__ pc, float*
     for (int pi = 0; pi < n_phi_iter; ++pi, phi += phi_step) {
         float c[kInterpT];
 #pragma unroll
-        for (int t = 0; t < kInterpT; ++t) c[t] = coef[phi * kInterpT + t];
+        for (int t = 0; t < kInterpT; ++t) c[t] = (n_phi_iter == 1) ? c0[t] : coef[phi * kInterpT + t];
         const int b_t = min(b, (own_hi - phi + U - 1) >> lu);     // iota with iota*U + phi < own_hi
         float w[kInterpT];
 #pragma unroll
@@ -677,8 +687,10 @@ fused_interp_kernel(const FusedParams prm) {
     float2* ex = (float2*)smem_raw;
     float2* Zs = ex + 4096;
     float* Pc = (float*)(Zs + kMaxClassScales * kBins);
+    int* s_ids = (int*)(Pc + 2 * kPcStride);
 
     const int tid = threadIdx.x;
+    if (tid < prm.n_scales) s_ids[tid] = prm.scale_ids[tid];
     const int r = tid & 15;
     const int g = tid >> 4;
     const int col = r & 7;             // coarse column: chunk-local sample (8 n1 + col) * U
@@ -711,7 +723,7 @@ fused_interp_kernel(const FusedParams prm) {
 #pragma unroll
         for (int k = 0; k < kChunkDec / 256; ++k) ex[tid + 256 * k] = make_float2(raw[k], 0.f);
         __syncthreads();
-        float2* Y = smem_fft_forward<5>(ex, ex + kChunkDec, prm.twf);
+        float2* Y = smem_fft1024_forward(ex, ex + kChunkDec, prm.twf);
         const float2 y = Y[tid];
         for (int s = 0; s < prm.n_scales; ++s) Zs[s * kBins + tid] = cmul(y, prm.table[s * kBins + tid]);
     }
@@ -723,6 +735,16 @@ fused_interp_kernel(const FusedParams prm) {
     }
     __syncthreads();
 
+    // taps of this thread's phase (one phase per thread while U <= 256): fetched once per block
+    float c0[kInterpT];
+    if (lu >= 4 && lu <= 8) {
+        const int phi0 = tid & ((1 << lu) - 1);
+#pragma unroll
+        for (int t = 0; t < kInterpT; ++t) c0[t] = __ldg(prm.coef + phi0 * kInterpT + t);
+    } else {
+#pragma unroll
+        for (int t = 0; t < kInterpT; ++t) c0[t] = 0.f;
+    }
     float* const out_c = (float*)prm.out + c * prm.c_stride + t0;
     for (int pair = 0; pair < prm.n_scales; pair += 2) {
         const int s = min(pair + sidx, prm.n_scales - 1);
@@ -747,8 +769,8 @@ fused_interp_kernel(const FusedParams prm) {
         // (3) polyphase interpolation + epilogue for the one or two scales of the pair
         for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl) {
             const float* pcs = Pc + sl * kPcStride;
-            float* row = out_c + (int64_t)prm.scale_ids[pair + sl] * prm.s_stride;
-            if (lu >= 4) interp_rows<KIND>(pcs, row, prm.coef, lu, ia, ib, own_hi);
+            float* row = out_c + (int64_t)s_ids[pair + sl] * prm.s_stride;
+            if (lu >= 4) interp_rows<KIND>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi);
             else if (lu == 3) interp_rows_small<KIND, 3>(pcs, row, ia, ib, own_hi);
             else if (lu == 2) interp_rows_small<KIND, 2>(pcs, row, ia, ib, own_hi);
             else interp_rows_small<KIND, 1>(pcs, row, ia, ib, own_hi);
