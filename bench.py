@@ -39,6 +39,13 @@ WORKLOADS = {
     # per GPU) exceeds HBM, so it is produced in time tiles into a reused buffer (tile = samples per tile)
     "cfg3": dict(fs=30000.0, n=18000000, channels=32, freq_limits=[1.7, 15000.0], vpo=10, output="power",
                  tile=2250000, desc="32ch/GPU x 30kHz x 10min, 128 scales, fp32 power, streamed in 8 time tiles"),
+    # config 4 of BASELINE.json: one 24 h recording at 30 kHz (2.592e9 samples) time-sharded over 8 GPUs
+    # = 3.24e8 samples per GPU; every step does the mean all-reduce, the NCCL halo exchange with both
+    # neighbours and the tiled transform of the shard
+    "cfg4": dict(fs=30000.0, n=324000000, channels=1, freq_limits=[1.7, 15000.0], vpo=10, output="power",
+                 tile=36000000, time_shard=True, plan_n=2592000000,
+                 desc="1ch x 30kHz, 3.24e8 samples per GPU (24 h over 8 GPUs), 128 scales, fp32 power, "
+                      "time-sharded with NCCL halos, streamed in time tiles"),
 }
 
 
@@ -62,7 +69,8 @@ def plan_frequencies(wl):
     cwt = ContinuousWaveletTransform(dtype=np.float32)
     cwt.fs = wl["fs"]
     cwt.wavelet.fs = wl["fs"]
-    return np.asarray(cwt.plan_frequencies(wl["n"], freq_limits=wl["freq_limits"], voices_per_octave=wl["vpo"]))
+    return np.asarray(cwt.plan_frequencies(wl.get("plan_n", wl["n"]), freq_limits=wl["freq_limits"],
+                                           voices_per_octave=wl["vpo"]))
 
 
 # --------------------------------------------------------------------------- clocks
@@ -199,7 +207,11 @@ def run_ours(args):
 
     # synthetic channels of this rank (channel shard: rank r owns channels r*nch .. r*nch+nch-1);
     # distinct seeds for the first 8, then reuse (generation cost only)
-    base = [synth.chirp_pink(n, fs, rank * nch + c, np.float32) for c in range(min(nch, 8))]
+    if n > 50000000:       # very long shards: tile a 2^24-sample block (generation cost only)
+        blk = [synth.chirp_pink(1 << 24, fs, rank * nch + c, np.float32) for c in range(min(nch, 8))]
+        base = [np.tile(b, n // b.size + 1)[:n] for b in blk]
+    else:
+        base = [synth.chirp_pink(n, fs, rank * nch + c, np.float32) for c in range(min(nch, 8))]
     x_host = torch.empty((nch, n), dtype=torch.float32).pin_memory()
     for c in range(nch):
         x_host[c] = torch.from_numpy(base[c % len(base)])
@@ -212,7 +224,10 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
 
     def one_pass():
-        if tile:
+        if wl.get("time_shard"):
+            from ghost_b200 import sharding
+            sharding.run_time_shard_tiled(plan, x_dev, rank, world, tile, out=out)
+        elif tile:
             plan.execute_tiled(x_dev, tile, out=out, means=step_means)
         else:
             plan.execute(x_dev, out)
@@ -321,7 +336,9 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "channels_per_gpu": nch, "samples": n,
-                       "scales": S, "fs": fs, "output": wl["output"], "parallelism": "channel-shard x%d" % world,
+                       "scales": S, "fs": fs, "output": wl["output"],
+                       "parallelism": ("time-shard x%d (NCCL halo exchange + mean all-reduce per step)" if wl.get("time_shard")
+                                       else "channel-shard x%d") % world,
                        "l2_policy": "inputs (%.2f GB) and outputs (%.1f GB) per step exceed the 126 MB L2" % (
                            nch * n * 4 / 1e9, coeffs_rank * out_el / 1e9),
                        "scale_classes": {"band_limited_interpolated": n_interp, "band_limited": n_banded,

@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = ["channel_block", "time_block", "global_means", "exchange_halos", "run_channel_shard",
-           "run_time_shard", "required_halo"]
+           "run_time_shard", "run_time_shard_tiled", "required_halo"]
 
 
 def _dist():
@@ -129,3 +129,27 @@ def run_time_shard(plan, core, rank, world, out=None, group=None):
     plan.execute(padded, out, means=means, start=hl, stop=hl + n_local, halo_left=hl, halo_right=hr,
                  out_start=0)
     return out
+
+
+def run_time_shard_tiled(plan, core, rank, world, tile, out=None, consumer=None, group=None):
+    """As :func:`run_time_shard` for shards whose coefficients do not fit in device memory: after
+    the mean all-reduce and the halo exchange the shard is transformed in time tiles into a
+    reused (channels, scales, tile) buffer (see ``CwtPlan.execute_tiled``).  Returns the number
+    of coefficients produced on this rank."""
+    n_local = core.shape[1]
+    sums = plan.channel_means(core) * float(n_local)
+    means = global_means(sums, n_local, group)
+    padded, hl, hr = exchange_halos(core, required_halo(plan), rank, world, group)
+    tile = int(min(tile, n_local))
+    if out is None:
+        out = plan.alloc_out(core.shape[0], tile)
+    halo = required_halo(plan)
+    done = 0
+    for a in range(0, n_local, tile):
+        b = min(n_local, a + tile)
+        plan.execute(padded, out, means=means, start=hl + a, stop=hl + b,
+                     halo_left=min(halo, hl + a), halo_right=min(halo, n_local - b + hr), out_start=0)
+        if consumer is not None:
+            consumer(out, a, b)
+        done += (b - a) * core.shape[0] * plan.n_scales
+    return done

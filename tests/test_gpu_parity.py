@@ -315,6 +315,28 @@ def test_time_shards_with_halos_equal_whole(dtype, bar):
     assert (np.max(np.abs(bad - whole), axis=1) / np.max(np.abs(whole), axis=1)).max() > 1e-3
 
 
+def test_tiled_execution_equals_whole():
+    """Results larger than HBM are produced in time tiles with real-sample halos
+    (CwtPlan.execute_tiled): every tile must equal the same columns of the whole transform."""
+    fs, n, tile = 1000.0, 100000, 30000
+    X = synth.recording(2, n, fs, np.float32) + 1.5
+    f = orc.frequency_grid(fs, 50000)
+    plan, L = _plan_for(3, 20, fs, f, dtype=np.float32, output="power")
+    xd = torch.from_numpy(X).cuda()
+    whole = plan.execute(xd)
+    seen = []
+
+    def consumer(out, a, b):
+        num = torch.linalg.vector_norm(out[:, :, :b - a] - whole[:, :, a:b], dim=2)
+        den = torch.linalg.vector_norm(whole[:, :, a:b], dim=2)
+        seen.append((a, b, float((num / den).max())))
+
+    count = plan.execute_tiled(xd, tile, consumer=consumer)
+    assert count == 2 * len(f) * n
+    assert [(a, b) for a, b, _ in seen] == [(0, 30000), (30000, 60000), (60000, 90000), (90000, 100000)]
+    assert max(e for _, _, e in seen) <= 4e-6, seen
+
+
 # ------------------------------------------------------------------ host-pointer ABI
 def test_execute_host_entry_point():
     fs, n = 1000.0, 12000
