@@ -187,6 +187,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")                  # keep NCCL's banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -251,12 +253,18 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    step_wall = []
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         one_pass()
+        step_wall.append(time.perf_counter() - t_s)
     ev1.record()
     barrier()
     sampler.stop_flag = True
     ms_total = ev0.elapsed_time(ev1)
+    if os.environ.get("GCWT_BENCH_VERBOSE"):
+        print("rank %d host ms per step (launch side): %s; device total %.1f ms" % (
+            rank, ["%.1f" % (t * 1e3) for t in step_wall], ms_total), file=sys.stderr, flush=True)
     launches = _lib.launch_count()
     prof = plan.profile_read(reset=True)
     plan.profile(False)
