@@ -305,7 +305,12 @@ __global__ void __launch_bounds__(256)
 pyramid_kernel(const TIn* __restrict__ in, int64_t in_stride, int64_t in_lo, int64_t in_hi,
                const double* __restrict__ means, float* __restrict__ out, int64_t out_stride,
                int64_t out_lo, int64_t out_len) {
-    __shared__ float tile[2 * kPyrTile + 2 * kHalfbandT + 2];
+    // The tile of 2*kPyrTile + 2T inputs is kept de-interleaved: ev[i] = input(u0 + 2i),
+    // od[i] = input(u0 + 2i + 1).  With T odd every tap of output j reads ev[j + const] and the
+    // centre reads od[j + const]: consecutive lanes hit consecutive banks (no conflicts).
+    constexpr int kHalf = kPyrTile + kHalfbandT + 1;
+    __shared__ float ev[kHalf];
+    __shared__ float od[kHalf];
     const int c = blockIdx.y;
     const int64_t i0 = out_lo + (int64_t)blockIdx.x * kPyrTile;     // first output index of the block
     const int64_t u0 = 2 * i0 - kHalfbandT;                         // first input index needed
@@ -315,19 +320,20 @@ pyramid_kernel(const TIn* __restrict__ in, int64_t in_stride, int64_t in_lo, int
         const int64_t u = u0 + k;
         float v = 0.f;
         if (u >= in_lo && u < in_hi) v = FIRST ? (float)((double)src[u] - mu) : (float)src[u];
-        tile[k] = v;
+        if (k & 1) od[k >> 1] = v; else ev[k >> 1] = v;
     }
     __syncthreads();
+    constexpr int kMid = (kHalfbandT - 1) / 2;                      // centre sample 2j + T = od[j + kMid]
     for (int j = threadIdx.x; j < kPyrTile; j += blockDim.x) {
         const int64_t i = i0 + j;
         if (i - out_lo >= out_len) break;
-        const int ctr = 2 * j + kHalfbandT;
+        // tap t = 2k+1 reads inputs 2j + T -+ t = ev[j + (T -+ t) / 2]
         // fp32 accumulation, smallest taps first (fp64 would spend the kernel on conversions)
         float acc = 0.f;
 #pragma unroll
         for (int k = kHalfbandOdd - 1; k >= 0; --k)
-            acc = fmaf(c_halfband[k], tile[ctr - (2 * k + 1)] + tile[ctr + (2 * k + 1)], acc);
-        acc = fmaf(0.5f, tile[ctr], acc);
+            acc = fmaf(c_halfband[k], ev[j + kMid - k] + ev[j + kMid + 1 + k], acc);
+        acc = fmaf(0.5f, od[j + kMid], acc);
         out[(int64_t)c * out_stride + (i - out_lo)] = acc;
     }
 }
