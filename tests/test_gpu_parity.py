@@ -133,7 +133,9 @@ def test_golden_cfg1_samples_fp32_and_fp64(golden_dir):
 # ------------------------------------------------------------------ oracle comparisons
 @pytest.mark.parametrize("gamma,beta,vpo,n", [(3, 20, 10, 16384), (1, 1, 4, 8192), (2, 10, 8, 10000),
                                               (3, 80, 16, 12000), (6, 3, 6, 9000), (9, 40, 12, 20000),
-                                              (3, 20, 48, 6000)])
+                                              (3, 20, 48, 6000), (3, 20, 48, 262144), (1, 20, 6, 30000),
+                                              (2, 5, 10, 262144), (9, 80, 8, 40000), (6, 40, 20, 50000),
+                                              (3, 1, 4, 16000), (1, 80, 4, 25000)])
 def test_fp64_complex_sweep(gamma, beta, vpo, n):
     """Config 5: fp64 complex coefficients over gamma/beta and voices-per-octave."""
     fs = 2000.0
@@ -143,6 +145,8 @@ def test_fp64_complex_sweep(gamma, beta, vpo, n):
     cwt = ContinuousWaveletTransform(wavelet=Morse(gamma=gamma, beta=beta), output="complex")
     cwt.transform(x, fs=fs, voices_per_octave=vpo)
     assert cwt.frequencies.tolist() == f.tolist()
+    if (vpo, n) == (48, 262144):
+        assert len(f) >= 500                                   # config 5's upper scale count
     err = _maxrel(cwt.coefficients, W)
     assert err.max() <= FP64_BAR, (int(np.argmax(err)), err.max())
 
