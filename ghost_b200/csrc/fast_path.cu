@@ -493,7 +493,7 @@ __device__ __forceinline__ void smem_fft4096_forward(float2* x, float2* y, const
 // smem: ex[2][4096] | Zs[kMaxClassScales][256] | Estep[256]
 constexpr size_t kBandedSmem = sizeof(float2) * (2 * 4096 + kMaxClassScales * kBins + kBins) + sizeof(int) * kMaxClassScales;
 
-template <int KIND>
+template <int KIND, int LP>       // LP > 0: compile-time log2(P) (store offsets become immediates)
 __global__ void __launch_bounds__(256, 2)
 fused_banded_kernel(const FusedParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -554,7 +554,7 @@ fused_banded_kernel(const FusedParams prm) {
 
     typedef typename out_elem<KIND>::type OutT;
     const int iters = min(prm.iters, prm.p_cols / 16 - unit * prm.iters);
-    const int lp = prm.log2p;
+    const int lp = LP > 0 ? LP : prm.log2p;
     const int own_lo = (int)prm.offset;
     const int own_hi = (int)min(prm.offset + prm.hop, prm.n - t0);       // chunk-local, <= nc_full
     const int64_t kstride = (int64_t)16 << lp;
@@ -596,10 +596,11 @@ fused_banded_kernel(const FusedParams prm) {
 constexpr int kPcStride = kCoarse + 16;           // % 32 == 16: the two scales of a pair hit different banks
 constexpr size_t kInterpSmem = sizeof(float2) * (4096 + kMaxClassScales * kBins) + sizeof(float) * 2 * kPcStride + sizeof(int) * kMaxClassScales;
 
-template <int KIND>
+template <int KIND, int LU>      // LU > 0: compile-time log2 of the coarse spacing (store offsets become immediates)
 __device__ __forceinline__ void interp_rows(const float* __restrict__ pc, float* __restrict__ row,
-                                            const float* __restrict__ coef, const float* c0, int lu,
+                                            const float* __restrict__ coef, const float* c0, int lu_rt,
                                             int ia, int ib, int own_hi) {
+    const int lu = LU > 0 ? LU : lu_rt;
     // thread <-> phase phi; lanes of a warp hold consecutive phases of the same coarse interval,
     // so the window loads are shared-memory broadcasts and the stores are contiguous.
     const int U = 1 << lu;
@@ -776,7 +777,18 @@ fused_interp_kernel(const FusedParams prm) {
         for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl) {
             const float* pcs = Pc + sl * kPcStride;
             float* row = out_c + (int64_t)s_ids[pair + sl] * prm.s_stride;
-            if (lu >= 4) interp_rows<KIND>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi);
+            if (lu >= 4) {
+                switch (lu) {
+                    case 4:  interp_rows<KIND, 4>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
+                    case 5:  interp_rows<KIND, 5>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
+                    case 6:  interp_rows<KIND, 6>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
+                    case 7:  interp_rows<KIND, 7>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
+                    case 8:  interp_rows<KIND, 8>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
+                    case 9:  interp_rows<KIND, 9>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
+                    case 10: interp_rows<KIND, 10>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
+                    default: interp_rows<KIND, 0>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
+                }
+            }
             else if (lu == 3) interp_rows_small<KIND, 3>(pcs, row, ia, ib, own_hi);
             else if (lu == 2) interp_rows_small<KIND, 2>(pcs, row, ia, ib, own_hi);
             else interp_rows_small<KIND, 1>(pcs, row, ia, ib, own_hi);
@@ -901,6 +913,31 @@ fused_full_kernel(const FusedParams prm) {
 }
 
 // ============================================================================ driver
+template <int KIND, int LP>
+static void launch_banded_one(unsigned nblk, cudaStream_t st, const FusedParams& prm) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaFuncSetAttribute(fused_banded_kernel<KIND, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem);
+        attr_set[dev & 63] = true;
+    }
+    fused_banded_kernel<KIND, LP><<<nblk, 256, kBandedSmem, st>>>(prm);
+}
+
+static void launch_banded(int kind, int lp, unsigned nblk, cudaStream_t st, const FusedParams& prm) {
+    if (kind == GCWT_OUT_COMPLEX) {
+        if (lp == 4) launch_banded_one<GCWT_OUT_COMPLEX, 4>(nblk, st, prm);
+        else launch_banded_one<GCWT_OUT_COMPLEX, 0>(nblk, st, prm);
+    } else if (kind == GCWT_OUT_AMPLITUDE) {
+        if (lp == 4) launch_banded_one<GCWT_OUT_AMPLITUDE, 4>(nblk, st, prm);
+        else launch_banded_one<GCWT_OUT_AMPLITUDE, 0>(nblk, st, prm);
+    } else {
+        if (lp == 4) launch_banded_one<GCWT_OUT_POWER, 4>(nblk, st, prm);
+        else launch_banded_one<GCWT_OUT_POWER, 0>(nblk, st, prm);
+    }
+}
+
 template <typename TIn, int KIND>
 static void launch_full_kind(unsigned nblk, cudaStream_t st, const FusedParams& prm) {
     static bool attr_set[64] = {false};
@@ -1007,14 +1044,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.units_per_chunk = (blocks + prm.iters - 1) / prm.iters;
             const int64_t nblk = n_channels * prm.n_chunks * prm.units_per_chunk;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
-            switch (p->out_kind) {
-                case GCWT_OUT_COMPLEX:
-                    fused_banded_kernel<GCWT_OUT_COMPLEX><<<(unsigned)nblk, 256, kBandedSmem, st>>>(prm); break;
-                case GCWT_OUT_AMPLITUDE:
-                    fused_banded_kernel<GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kBandedSmem, st>>>(prm); break;
-                default:
-                    fused_banded_kernel<GCWT_OUT_POWER><<<(unsigned)nblk, 256, kBandedSmem, st>>>(prm); break;
-            }
+            launch_banded(p->out_kind, prm.log2p, (unsigned)nblk, st, prm);
         } else {
             prm.src = x; prm.src_stride = x_stride; prm.src_lo = -halo_l; prm.src_hi = n + halo_r;
             prm.log2d = 0; prm.p_cols = 16; prm.log2p = 4; prm.iters = 1; prm.units_per_chunk = 1;
@@ -1033,9 +1063,6 @@ static bool g_attr_done[64] = {false};
 
 template <typename TIn>
 static int set_smem_attrs() {
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_banded_kernel<GCWT_OUT_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_banded_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_banded_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
     return GCWT_OK;
