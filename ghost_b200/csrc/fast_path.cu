@@ -798,14 +798,12 @@ fused_interp_kernel(const FusedParams prm) {
 }
 
 // ---------------------------------------------------------------------------- full spectrum
-// smem: Yf[4096] | ex[4096] | A[4096] | T[8*256] (next scale's table rows) | ids[64] | nmu[64]
-constexpr int kStageMu = 8;       // table rows of scales occupying <= 8 blocks are staged ahead
-constexpr size_t kFullSmem = sizeof(float2) * (3 * 4096 + kStageMu * 256) + sizeof(int) * 2 * kMaxFullScales;
+// smem: Yf[4096] | ex[4096] | A[4096] | ids[64] | nmu[64]
+constexpr size_t kFullSmem = sizeof(float2) * 3 * 4096 + sizeof(int) * 2 * kMaxFullScales;
 
 // radix-16 over the aliases m' + 256 mu of spectrum bin m' = tid, pruned to the first NMU
 // aliases (the others are empty for a filter that occupies only NMU blocks of 256 bins)
-// `tab` points at this thread's first table entry: in shared memory (staged by cp.async, stride
-// 256) for NMU <= kStageMu, in global memory otherwise.
+// `tab` points at this thread's first table entry (global memory, stride 256).
 template <int NMU>
 __device__ __forceinline__ void full_prepass(const float2* __restrict__ Yf, const float2* __restrict__ tab,
                                              float2* __restrict__ A, const float2* tw4k) {
@@ -813,7 +811,7 @@ __device__ __forceinline__ void full_prepass(const float2* __restrict__ Yf, cons
     float2 a[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k)
-        a[k] = (k < NMU) ? cmul(Yf[tid + 256 * k], tab[256 * k]) : make_float2(0.f, 0.f);
+        a[k] = (k < NMU) ? cmul(Yf[tid + 256 * k], __ldg(tab + 256 * k)) : make_float2(0.f, 0.f);
     dft16<+1>(a);
 #pragma unroll
     for (int k = 0; k < 16; ++k) A[tid * 16 + (k ^ (tid & 15))] = k ? cmul(a[k], tw4k[k]) : a[k];
@@ -826,8 +824,7 @@ fused_full_kernel(const FusedParams prm) {
     float2* Yf = (float2*)smem_raw;      // order matters: the forward FFT's padded pass spills 2 KB into ex
     float2* ex = Yf + kFullN;
     float2* A = ex + kFullN;
-    float2* T = A + kFullN;              // T[tid + 256 k]: private to thread tid, filled by cp.async
-    int* s_ids = (int*)(T + kStageMu * 256);
+    int* s_ids = (int*)(A + kFullN);
     int* s_nmu = s_ids + kMaxFullScales;
 
     const int tid = threadIdx.x;
@@ -867,30 +864,16 @@ fused_full_kernel(const FusedParams prm) {
     OutT* const out_c = (OutT*)prm.out + c * prm.c_stride + t0;
     if (tid < prm.n_scales) { s_ids[tid] = prm.scale_ids[tid]; s_nmu[tid] = prm.scale_nmu[tid]; }
     __syncthreads();
-    // stage the table rows of scale `sn` (those this thread will read) into T
-    auto stage = [&](int sn) {
-        if (sn < prm.n_scales) {
-            const int nm = s_nmu[sn];
-            if (nm <= kStageMu) {
-                const float2* src = prm.table + (int64_t)sn * kFullN + tid;
-                for (int k = 0; k < nm; ++k) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(T + tid + 256 * k);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src + 256 * k) : "memory");
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    stage(0);
     for (int s = 0; s < prm.n_scales; ++s) {
         float2 a[16];
         const int nmu = s_nmu[s];
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (nmu == 2) full_prepass<2>(Yf, T + tid, A, tw4k);
-        else if (nmu == 4) full_prepass<4>(Yf, T + tid, A, tw4k);
-        else if (nmu == 8) full_prepass<8>(Yf, T + tid, A, tw4k);
-        else full_prepass<16>(Yf, prm.table + (int64_t)s * kFullN + tid, A, tw4k);
-        stage(s + 1);                                             // lands while this scale is transformed
+        // the table rows stream from L2 through L1: this kernel is co-limited by the LSU data pipe,
+        // and staging them through shared memory (cp.async) costs a second LSU operation per entry
+        const float2* tab = prm.table + (int64_t)s * kFullN + tid;
+        if (nmu == 2) full_prepass<2>(Yf, tab, A, tw4k);
+        else if (nmu == 4) full_prepass<4>(Yf, tab, A, tw4k);
+        else if (nmu == 8) full_prepass<8>(Yf, tab, A, tw4k);
+        else full_prepass<16>(Yf, tab, A, tw4k);
         __syncthreads();
         // pass 1 of the 256-point transforms (16 columns)
 #pragma unroll
