@@ -173,6 +173,7 @@ int gcwt_plan_destroy(gcwt_plan* p) {
     if (p->d_terms) cudaFree(p->d_terms);
     if (p->ws.ptr) cudaFree(p->ws.ptr);
     if (p->d_means) cudaFree(p->d_means);
+    if (p->d_partial) cudaFree(p->d_partial);
     if (p->d_twiddle) cudaFree(p->d_twiddle);
     delete p;
     return GCWT_OK;
@@ -209,7 +210,13 @@ int gcwt_channel_means(const void* x, int32_t in_type, int64_t n_channels, int64
     if (!x || !means_dev) { set_error("channel_means: NULL argument"); return GCWT_ERR_ARG; }
     if (in_type != GCWT_F32 && in_type != GCWT_F64) { set_error("channel_means: bad in_type"); return GCWT_ERR_ARG; }
     GCWT_CUDA_OK(cudaSetDevice(device));
-    return means_launch(x, in_type, n_channels, n_samples, x_stride, means_dev, (cudaStream_t)stream);
+    // stand-alone call: scratch is allocated and freed here (synchronous; not on the transform path)
+    double* partial = nullptr;
+    GCWT_CUDA_OK(cudaMalloc((void**)&partial, sizeof(double) * means_blocks(n_samples) * n_channels));
+    int rc = means_launch(x, in_type, n_channels, n_samples, x_stride, means_dev, partial, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(partial);
+    return rc;
 }
 
 int gcwt_execute(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_channels, int64_t n_samples,
@@ -228,8 +235,15 @@ int gcwt_execute(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_channel
             GCWT_CUDA_OK(cudaMalloc((void**)&p->d_means, sizeof(double) * n_channels));
             p->means_cap = n_channels;
         }
+        const int64_t need = (int64_t)means_blocks(n_samples) * n_channels;
+        if (p->partial_cap < need) {
+            if (p->d_partial) cudaFree(p->d_partial);
+            p->d_partial = nullptr; p->partial_cap = 0;
+            GCWT_CUDA_OK(cudaMalloc((void**)&p->d_partial, sizeof(double) * need));
+            p->partial_cap = need;
+        }
         const int sp = prof_begin(p, 0, st);
-        rc = means_launch(x, in_type, n_channels, n_samples, x_stride, p->d_means, st);
+        rc = means_launch(x, in_type, n_channels, n_samples, x_stride, p->d_means, p->d_partial, st);
         prof_end(p, sp, st);
         if (rc) return rc;
         d_means = p->d_means;

@@ -43,13 +43,17 @@ __global__ void mean_final_kernel(const double* __restrict__ partial, int nb, in
     means[c] = acc / (double)n;
 }
 
-int means_launch(const void* x, int in_type, int64_t n_channels, int64_t n_samples,
-                 int64_t x_stride, double* d_means, cudaStream_t st) {
-    if (n_channels <= 0 || n_samples <= 0) { set_error("means: empty input"); return GCWT_ERR_ARG; }
+int means_blocks(int64_t n_samples) {
     int nb = (int)std::min<int64_t>(512, (n_samples + 4095) / 4096);
-    if (nb < 1) nb = 1;
-    double* partial = nullptr;
-    GCWT_CUDA_OK(cudaMallocAsync((void**)&partial, sizeof(double) * nb * n_channels, st));
+    return nb < 1 ? 1 : nb;
+}
+
+// `partial` is scratch for means_blocks(n_samples) * n_channels doubles (no allocation on the hot path:
+// stream-ordered allocations here showed up as milliseconds of jitter per transform)
+int means_launch(const void* x, int in_type, int64_t n_channels, int64_t n_samples,
+                 int64_t x_stride, double* d_means, double* partial, cudaStream_t st) {
+    if (n_channels <= 0 || n_samples <= 0) { set_error("means: empty input"); return GCWT_ERR_ARG; }
+    const int nb = means_blocks(n_samples);
     dim3 grid(nb, (unsigned)n_channels);
     if (in_type == GCWT_F32)
         mean_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, n_samples, x_stride, partial);
@@ -59,7 +63,6 @@ int means_launch(const void* x, int in_type, int64_t n_channels, int64_t n_sampl
                                                                             (int)n_channels);
     count_launch(2);
     GCWT_CUDA_OK(cudaGetLastError());
-    GCWT_CUDA_OK(cudaFreeAsync(partial, st));
     return GCWT_OK;
 }
 

@@ -77,6 +77,8 @@ struct gcwt_plan {
     float2* d_twiddle = nullptr;            // e^{-2 pi i k / 4096}, k < 4096 (forward FFTs of the fused kernels)
     double* d_means = nullptr;              // internal per-channel means
     int64_t means_cap = 0;
+    double* d_partial = nullptr;            // scratch of the mean reduction
+    int64_t partial_cap = 0;
 };
 
 namespace gcwt {
@@ -98,6 +100,7 @@ int fast_execute(gcwt_plan* p, const void* x, int in_type,
                  void* out, int64_t s_stride, int64_t c_stride, cudaStream_t st);
 int fast_plan_build(gcwt_plan* p);       // classify scales + upload tables (fp32 plans)
 void fast_plan_free(gcwt_plan* p);
+int means_blocks(int64_t n_samples);
 int means_launch(const void* x, int in_type, int64_t n_channels, int64_t n_samples,
-                 int64_t x_stride, double* d_means, cudaStream_t st);
+                 int64_t x_stride, double* d_means, double* partial, cudaStream_t st);
 }  // namespace gcwt
