@@ -280,7 +280,9 @@ def run_ours(args):
     levels = plan.levels()
     out_el = 8 if wl["output"] == "complex" else 4
     interp_on = wl["output"] != "complex"
-    n_interp = int((levels >= 3).sum()) if interp_on else 0
+    # level 2 joins the interpolated classes when its bands allow the wide coarse grid (no direct launches then)
+    min_interp_level = 2 if prof["fused_banded"][1] == 0 else 3
+    n_interp = int((levels >= min_interp_level).sum()) if interp_on else 0
     n_banded = int((levels >= 0).sum()) - n_interp
     n_full = int((levels == -1).sum())
     fam_scales = {"fused_interp": n_interp, "fused_banded": n_banded, "fused_full": n_full}

@@ -35,6 +35,9 @@ __constant__ float c_halfband[kHalfbandOdd];
 // polyphase taps for the small coarse spacings U = 2, 4, 8 (constant-bank operands of the FMAs)
 constexpr int kSmallCoef = (2 + 4 + 8) * kInterpT;
 __constant__ float c_interp_small[kSmallCoef];
+// wide-spacing classes: U = 4 (level 2) and U = 8 (level 3), kWideT taps
+constexpr int kWideCoef = (4 + 8) * kWideT;
+__constant__ float c_interp_wide[kWideCoef];
 
 // ============================================================================ planner
 static double bessel_i0(double x) {
@@ -139,6 +142,20 @@ static int full_extent(const gcwt_plan* p, const PlanResponses& pr, int s) {
     return 16;
 }
 
+// Width (in bins of the level's grid) of the band that holds all but band_tol^2 of the filter's
+// energy: |W|^2 of this scale is band-limited to that many bins around zero frequency.
+static int band_width_bins(const gcwt_plan* p, const PlanResponses& pr, int s, int level) {
+    const double* g = pr.level(s, level);
+    const double e_tot = filter_energy(p, p->scales[s], (int64_t)kChunkDec << level);
+    const double budget = 0.5 * p->band_tol * p->band_tol * e_tot;
+    int lo = 0, hi = kBins - 1;
+    double acc = 0.0;
+    while (lo < hi && acc + g[lo] * g[lo] < budget) { acc += g[lo] * g[lo]; ++lo; }
+    acc = 0.0;
+    while (hi > lo && acc + g[hi] * g[hi] < budget) { acc += g[hi] * g[hi]; --hi; }
+    return hi - lo + 1;
+}
+
 static int choose_level(const gcwt_plan* p, const PlanResponses& pr, int s) {
     const ScaleInfo& sc = p->scales[s];
     if (!(p->flags & GCWT_FLAG_FORCE_GENERIC)) {
@@ -156,8 +173,9 @@ static void class_geometry(FastClass& fc) {
     const int64_t d = fc.level >= 0 ? (int64_t(1) << fc.level) : 1;
     const int64_t align = std::max<int64_t>(d, 16);
     // interpolated classes read kInterpT coarse samples around every output: keep them valid
-    const int64_t lead = fc.interp ? (int64_t)(kInterpT / 2 - 1) << fc.log2u : 0;
-    const int64_t tail = fc.interp ? (int64_t)(kInterpT / 2 + 1) << fc.log2u : 0;
+    const int taps = fc.wide ? kWideT : kInterpT;
+    const int64_t lead = fc.interp ? (int64_t)(taps / 2 - 1) << fc.log2u : 0;
+    const int64_t tail = fc.interp ? (int64_t)(taps / 2 + 1) << fc.log2u : 0;
     fc.offset = ((fc.lmax / 2 + lead + align - 1) / align) * align;
     fc.hop = ((fc.nc_full - (fc.lmax - 1) / 2 - tail - fc.offset) / align) * align;
 }
@@ -165,12 +183,12 @@ static void class_geometry(FastClass& fc) {
 // Kaiser-windowed sinc, kInterpT taps: output at coarse position iota + phi/U is
 // sum_t c[phi][t] * p[iota + t - (T/2 - 1)].  The interpolated signal |W|^2 is band-limited
 // to a quarter of the coarse Nyquist band or less, so a wide window (beta = 14) is right.
-static void design_interpolator(int log2u, std::vector<float>& coef) {
-    const int U = 1 << log2u, T = kInterpT;
+static void design_interpolator(int log2u, std::vector<float>& coef, int T = kInterpT) {
+    const int U = 1 << log2u;
     const double beta = 14.0, i0b = bessel_i0(beta);
     coef.resize((size_t)U * T);
     for (int phi = 0; phi < U; ++phi) {
-        double c[kInterpT], sum = 0.0;
+        double c[32], sum = 0.0;
         for (int t = 0; t < T; ++t) {
             const double tau = (double)phi / U - (double)(t - (T / 2 - 1));
             const double r = 2.0 * tau / T;
@@ -193,6 +211,12 @@ static int upload_constants(const gcwt_plan* p) {
         all.insert(all.end(), part.begin(), part.end());
     }
     GCWT_CUDA_OK(cudaMemcpyToSymbol(c_interp_small, all.data(), sizeof(float) * kSmallCoef));
+    all.clear();
+    for (int lu = 2; lu <= 3; ++lu) {
+        design_interpolator(lu, part, kWideT);
+        all.insert(all.end(), part.begin(), part.end());
+    }
+    GCWT_CUDA_OK(cudaMemcpyToSymbol(c_interp_wide, all.data(), sizeof(float) * kWideCoef));
     return GCWT_OK;
 }
 
@@ -236,9 +260,17 @@ int fast_plan_build(gcwt_plan* p) {
             fc.scale_ids.assign(ids.begin() + i0, ids.begin() + std::min(ids.size(), i0 + cap));
             fc.lmax = 1;
             for (int id : fc.scale_ids) fc.lmax = std::max(fc.lmax, p->scales[id].L);
-            fc.interp = level >= kInterpMinLevel && p->out_kind != GCWT_OUT_COMPLEX &&
-                        !(p->flags & GCWT_FLAG_NO_INTERP);
+            const bool may_interp = p->out_kind != GCWT_OUT_COMPLEX && !(p->flags & GCWT_FLAG_NO_INTERP);
+            fc.interp = level >= kInterpMinLevel && may_interp;
             fc.log2u = level - 1;
+            if (may_interp && level >= 2 && level <= kWideMaxLevel) {
+                // coarse spacing U = D is allowed when |W|^2 stays 2.5x over-sampled on that grid:
+                // band width w bins of the (1024 D)-point grid -> highest frequency 2 pi w / (1024 D);
+                // coarse Nyquist pi / D; ratio 512 / w
+                int wmax = 1;
+                for (int id : fc.scale_ids) wmax = std::max(wmax, band_width_bins(p, pr, id, level));
+                if (512.0 / (double)wmax >= 2.5) { fc.interp = true; fc.wide = true; fc.log2u = level; }
+            }
             class_geometry(fc);
             if (fc.hop <= 0) { set_error("planner: non-positive hop"); return GCWT_ERR_ARG; }
             const int nb = level >= 0 ? kBins : kFullN;
@@ -594,7 +626,9 @@ fused_banded_kernel(const FusedParams prm) {
 // moves these classes from the FP32-issue bound to the HBM bound.
 // smem: ex[4096] float2 | Zs[kMaxClassScales][256] float2 | Pc[2][kPcStride] float
 constexpr int kPcStride = kCoarse + 16;           // % 32 == 16: the two scales of a pair hit different banks
-constexpr size_t kInterpSmem = sizeof(float2) * (4096 + kMaxClassScales * kBins) + sizeof(float) * 2 * kPcStride + sizeof(int) * kMaxClassScales;
+constexpr int kPcStrideW = kCoarseWide + 40;      // % 32 == 8: the four scales of a quad hit different banks
+constexpr int kPcFloats = (2 * kPcStride > 4 * kPcStrideW) ? 2 * kPcStride : 4 * kPcStrideW;
+constexpr size_t kInterpSmem = sizeof(float2) * (4096 + kMaxClassScales * kBins) + sizeof(float) * kPcFloats + sizeof(int) * kMaxClassScales;
 
 template <int KIND, int LU>      // LU > 0: compile-time log2 of the coarse spacing (store offsets become immediates)
 __device__ __forceinline__ void interp_rows(const float* __restrict__ pc, float* __restrict__ row,
@@ -687,21 +721,55 @@ __device__ __forceinline__ void interp_rows_small(const float* __restrict__ pc, 
     }
 }
 
-template <int KIND>
+// Wide-spacing classes (coarse spacing U = D = 4 or 8, kWideT taps): thread <-> coarse interval,
+// all U phases from one register window, taps from the constant bank, 128-bit stores.
+template <int KIND, int LU>
+__device__ __forceinline__ void interp_rows_wide(const float* __restrict__ pc, float* __restrict__ row,
+                                                 int ia, int ib, int own_hi) {
+    constexpr int U = 1 << LU;
+    constexpr int COFF = (LU == 2) ? 0 : 4 * kWideT;
+    for (int iota = ia + (int)threadIdx.x; iota < ib; iota += 256) {
+        float w[kWideT];
+#pragma unroll
+        for (int j = 0; j < kWideT; ++j) w[j] = pc[iota - (kWideT / 2 - 1) + j];
+        float o[U];
+        o[0] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_approx(w[kWideT / 2 - 1]) : w[kWideT / 2 - 1];
+#pragma unroll
+        for (int phi = 1; phi < U; ++phi) {
+            float acc = c_interp_wide[COFF + phi * kWideT] * w[0];
+#pragma unroll
+            for (int j = 1; j < kWideT; ++j) acc = fmaf(c_interp_wide[COFF + phi * kWideT + j], w[j], acc);
+            o[phi] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_abs_approx(acc) : fmaxf(acc, 0.f);
+        }
+        float* op = row + (int64_t)iota * U;
+        if ((iota + 1) * U <= own_hi) {
+#pragma unroll
+            for (int v = 0; v < U / 4; ++v) ((float4*)op)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        } else {
+#pragma unroll
+            for (int phi = 0; phi < U; ++phi) if (iota * U + phi < own_hi) op[phi] = o[phi];
+        }
+    }
+}
+
+template <int KIND, bool WIDE>     // WIDE: 4 coarse columns (U = D), four scales per pass
 __global__ void __launch_bounds__(256, 2)
 fused_interp_kernel(const FusedParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* ex = (float2*)smem_raw;
     float2* Zs = ex + 4096;
     float* Pc = (float*)(Zs + kMaxClassScales * kBins);
-    int* s_ids = (int*)(Pc + 2 * kPcStride);
+    int* s_ids = (int*)(Pc + kPcFloats);
+    constexpr int NCOL = WIDE ? 4 : 8;             // coarse columns per chunk
+    constexpr int NSC = 16 / NCOL;                 // scales transformed per 16-lane pass
+    constexpr int PCS = WIDE ? kPcStrideW : kPcStride;
 
     const int tid = threadIdx.x;
     if (tid < prm.n_scales) s_ids[tid] = prm.scale_ids[tid];
     const int r = tid & 15;
     const int g = tid >> 4;
-    const int col = r & 7;             // coarse column: chunk-local sample (8 n1 + col) * U
-    const int sidx = r >> 3;           // which scale of the pair
+    const int col = r & (NCOL - 1);    // coarse column: chunk-local sample (NCOL n1 + col) * U
+    const int sidx = r / NCOL;         // which scale of the group
 
     int64_t bid = blockIdx.x;
     const int split = (int)(bid % prm.units_per_chunk); bid /= prm.units_per_chunk;
@@ -738,13 +806,13 @@ fused_interp_kernel(const FusedParams prm) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         tw[k] = tw_pos(prm.twf, 16 * g * k);                      // e^{2 pi i g k / 256}
-        R[k] = tw_pos(prm.twf, 2 * (g + 16 * k) * col);           // e^{2 pi i m col / 2048}
+        R[k] = tw_pos(prm.twf, (16 / NCOL) * (g + 16 * k) * col); // e^{2 pi i m col / (256 NCOL)}
     }
     __syncthreads();
 
     // taps of this thread's phase (one phase per thread while U <= 256): fetched once per block
     float c0[kInterpT];
-    if (lu >= 4 && lu <= 8) {
+    if (!WIDE && lu >= 4 && lu <= 8) {
         const int phi0 = tid & ((1 << lu) - 1);
 #pragma unroll
         for (int t = 0; t < kInterpT; ++t) c0[t] = __ldg(prm.coef + phi0 * kInterpT + t);
@@ -753,7 +821,7 @@ fused_interp_kernel(const FusedParams prm) {
         for (int t = 0; t < kInterpT; ++t) c0[t] = 0.f;
     }
     float* const out_c = (float*)prm.out + c * prm.c_stride + t0;
-    for (int pair = 0; pair < prm.n_scales; pair += 2) {
+    for (int pair = 0; pair < prm.n_scales; pair += NSC) {
         const int s = min(pair + sidx, prm.n_scales - 1);
         float2 a[16];
         const float2* z = Zs + s * kBins + g;
@@ -769,15 +837,18 @@ fused_interp_kernel(const FusedParams prm) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
         dft16<+1>(a);
-        float* pc = Pc + sidx * kPcStride + g * 8 + col;          // iota = (g + 16 k) * 8 + col
+        float* pc = Pc + sidx * PCS + g * NCOL + col;             // iota = (g + 16 k) * NCOL + col
 #pragma unroll
-        for (int k = 0; k < 16; ++k) pc[k * 128] = a[k].x * a[k].x + a[k].y * a[k].y;
+        for (int k = 0; k < 16; ++k) pc[k * 16 * NCOL] = a[k].x * a[k].x + a[k].y * a[k].y;
         __syncthreads();
-        // (3) polyphase interpolation + epilogue for the one or two scales of the pair
-        for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl) {
-            const float* pcs = Pc + sl * kPcStride;
+        // (3) polyphase interpolation + epilogue for the scales of this pass
+        for (int sl = 0; sl < NSC && pair + sl < prm.n_scales; ++sl) {
+            const float* pcs = Pc + sl * PCS;
             float* row = out_c + (int64_t)s_ids[pair + sl] * prm.s_stride;
-            if (lu >= 4) {
+            if (WIDE) {
+                if (lu == 2) interp_rows_wide<KIND, 2>(pcs, row, ia, ib, own_hi);
+                else interp_rows_wide<KIND, 3>(pcs, row, ia, ib, own_hi);
+            } else if (lu >= 4) {
                 switch (lu) {
                     case 4:  interp_rows<KIND, 4>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
                     case 5:  interp_rows<KIND, 5>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
@@ -996,6 +1067,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         // the small-spacing interpolator writes 128-bit vectors: rows must be 16-byte aligned
         const bool rows_aligned = ((uintptr_t)out % 16 == 0) && (s_stride % 4 == 0) && (c_stride % 4 == 0);
         if (fc.level >= 0 && fc.interp && (fc.log2u >= 4 || rows_aligned)) {
+            // (an unaligned wide class falls through to the direct kernel with its own geometry)
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
             prm.log2d = fc.level;
@@ -1012,10 +1084,15 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.units_per_chunk = (int)splits;
             const int64_t nblk = chunks * splits;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
-            if (p->out_kind == GCWT_OUT_AMPLITUDE)
-                fused_interp_kernel<GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
+            if (fc.wide) {
+                if (p->out_kind == GCWT_OUT_AMPLITUDE)
+                    fused_interp_kernel<GCWT_OUT_AMPLITUDE, true><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
+                else
+                    fused_interp_kernel<GCWT_OUT_POWER, true><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
+            } else if (p->out_kind == GCWT_OUT_AMPLITUDE)
+                fused_interp_kernel<GCWT_OUT_AMPLITUDE, false><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
             else
-                fused_interp_kernel<GCWT_OUT_POWER><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
+                fused_interp_kernel<GCWT_OUT_POWER, false><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
         } else if (fc.level >= 0) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1046,8 +1123,10 @@ static bool g_attr_done[64] = {false};
 
 template <typename TIn>
 static int set_smem_attrs() {
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
     return GCWT_OK;
 }
 

@@ -15,6 +15,9 @@ constexpr int kMinFastLevel = 2;    // P = kChunkDec * 2^level / kBins must be >
 constexpr int kInterpT = 10;        // taps of the polyphase interpolator (amplitude / power output)
 constexpr int kInterpMinLevel = 3;  // interpolated classes: coarse spacing U = 2^(level-1) >= 4
 constexpr int kCoarse = 2048;       // coarse |W|^2 samples per chunk and scale (8 columns x 256)
+constexpr int kWideT = 14;          // taps of the interpolator of the wide-spacing classes (U = D)
+constexpr int kWideMaxLevel = 3;    // levels 2 and 3 use U = D when their bands allow it
+constexpr int kCoarseWide = 1024;   // coarse samples per chunk and scale in those classes (4 columns x 256)
 constexpr int kHalfbandT = 19;      // half-band taps run from -T..T
 constexpr int kHalfbandOdd = (kHalfbandT + 1) / 2;
 
@@ -42,6 +45,7 @@ struct FastClass {
     std::vector<int> scale_nmu;     // full-spectrum kernel: occupied 256-bin blocks per scale (2, 4, 8, 16)
     int32_t* d_scale_nmu = nullptr;
     bool interp = false;
+    bool wide = false;              // coarse spacing U = D (4 columns), kWideT taps; else U = D/2, kInterpT taps
     int log2u = 0;
     float* d_coef = nullptr;
 };
