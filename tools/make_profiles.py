@@ -54,7 +54,7 @@ except FileNotFoundError:
 
 # ---- ncu summary + measured traffic -----------------------------------------------------------------
 subprocess.run([sys.executable, "tools/ncu_summary.py", G + "prof_fused_%s.ncu-rep" % tag, P + "%s_fused_kernels_ncu.md" % tag,
-                "Round %s - fused kernels (full, banded level 2, interp levels 3-8), config 2 with 16 channels" % tag], check=True)
+                "Round %s - fused kernels (one launch per scale class), config 2 with 16 channels" % tag], check=True)
 raw = subprocess.run(["ncu", "-i", G + "prof_fused_%s.ncu-rep" % tag, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
