@@ -21,7 +21,7 @@ EXPORTS = (
     "gcwt_plan_destroy", "gcwt_plan_levels", "gcwt_plan_workspace_bytes",
     "gcwt_channel_means", "gcwt_execute", "gcwt_execute_host", "gcwt_filter_response",
     "gcwt_morse_kernel", "gcwt_profile_enable", "gcwt_profile_read",
-    "gcwt_fastconv", "gcwt_dft", "gcwt_analytic_signal",
+    "gcwt_fastconv", "gcwt_dft", "gcwt_analytic_signal", "gcwt_moments",
 )
 
 
@@ -75,6 +75,7 @@ def load():
     lib.gcwt_fastconv.argtypes = [dp, i32, i64, dp, i32, i64, dp, i32]
     lib.gcwt_dft.argtypes = [dp, i64, i32, dp, i32]
     lib.gcwt_analytic_signal.argtypes = [dp, i64, dp, i32]
+    lib.gcwt_moments.argtypes = [vp, i32, i64, i32, dp, i32, vp]
     lib.gcwt_profile_enable.argtypes = [vp, i32]
     lib.gcwt_profile_read.argtypes = [vp, dp, C.POINTER(i64), i32]
     _lib = lib

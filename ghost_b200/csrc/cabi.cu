@@ -73,6 +73,8 @@ int sig_analytic_host(const double* x_host, int64_t n, double* out_host);
 int sig_fastconv_host(const double* sig_host, int sig_complex, int64_t n, const double* ker_host, int ker_complex,
                       int64_t m, double* out_host);
 
+int sig_moments(const void* x_dev, int type, int64_t n, int square, double* out_host, cudaStream_t st);
+
 static int check_exec_args(const gcwt_plan* plan, const void* x, int in_type, int64_t n_channels,
                            int64_t n_samples, int64_t x_stride, const void* out) {
     if (!plan) { set_error("plan is NULL"); return GCWT_ERR_ARG; }
@@ -341,6 +343,13 @@ int gcwt_dft(const double* x_complex, int64_t n, int32_t sign, double* out_compl
     if (!x_complex || !out_complex || n < 1 || (sign != 1 && sign != -1)) { set_error("dft: bad argument"); return GCWT_ERR_ARG; }
     GCWT_CUDA_OK(cudaSetDevice(device));
     return sig_dft_host(x_complex, n, sign, out_complex);
+}
+
+int gcwt_moments(const void* x_dev, int32_t type, int64_t n, int32_t square, double* out_host, int32_t device,
+                 void* stream) {
+    if (!x_dev || !out_host || n < 1 || (type != GCWT_F32 && type != GCWT_F64)) { set_error("moments: bad argument"); return GCWT_ERR_ARG; }
+    GCWT_CUDA_OK(cudaSetDevice(device));
+    return sig_moments(x_dev, type, n, square, out_host, (cudaStream_t)stream);
 }
 
 int gcwt_analytic_signal(const double* x, int64_t n, double* out_complex, int32_t device) {

@@ -196,4 +196,47 @@ int sig_fastconv_host(const double* sig_host, int sig_complex, int64_t n, const 
     return GCWT_OK;
 }
 
+// ---------------------------------------------------------------------------- moments
+// sum and sum of squares (of x, or of x^2 when `square`) in fp64: the global mean / std that
+// plot(standardize=True) needs (ghost/wave/transforms.py:360-366) without a host pass.
+template <typename T>
+__global__ void moments_kernel(const T* __restrict__ x, int64_t n, int square, double* __restrict__ acc) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = (double)x[i];
+        if (square) v *= v;
+        s1 += v;
+        s2 += v * v;
+    }
+    __shared__ double sh1[256], sh2[256];
+    sh1[threadIdx.x] = s1; sh2[threadIdx.x] = s2;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) { sh1[threadIdx.x] += sh1[threadIdx.x + k]; sh2[threadIdx.x] += sh2[threadIdx.x + k]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { atomicAdd(acc, sh1[0]); atomicAdd(acc + 1, sh2[0]); }
+}
+
+int sig_moments(const void* x_dev, int type, int64_t n, int square, double* out_host, cudaStream_t st) {
+    double* d = nullptr;
+    GCWT_CUDA_OK(cudaMalloc((void**)&d, 2 * sizeof(double)));
+    GCWT_CUDA_OK(cudaMemsetAsync(d, 0, 2 * sizeof(double), st));
+    const unsigned blocks = (unsigned)std::min<int64_t>(148 * 8, (n + 255) / 256);
+    if (type == GCWT_F32) moments_kernel<float><<<blocks, 256, 0, st>>>((const float*)x_dev, n, square, d);
+    else moments_kernel<double><<<blocks, 256, 0, st>>>((const double*)x_dev, n, square, d);
+    count_launch();
+    GCWT_CUDA_OK(cudaGetLastError());
+    double h[2];
+    GCWT_CUDA_OK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GCWT_CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(d);
+    const double mean = h[0] / (double)n;
+    double var = h[1] / (double)n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    out_host[0] = mean;
+    out_host[1] = sqrt(var);
+    return GCWT_OK;
+}
+
 }  // namespace gcwt

@@ -372,10 +372,39 @@ class ContinuousWaveletTransform(WaveletTransform):
             raise ValueError("plotting needs a single-channel transform")
         time_slice = slice(None) if time_limits is None else self._restrict_plot_time(np.array(time_limits))
         freq_slice = slice(None) if freq_limits is None else self._restrict_plot_freq(freq_limits)
+        if self._result is not None and self._host is None and self._output in ("amplitude", "power") \
+                and (self._output == kind or (self._output == "amplitude" and kind == "power")):
+            # result still on the device (keep_on_device=True): global moments there, and only the
+            # requested window is copied to the host
+            win = self._result[0][freq_slice, time_slice].cpu().numpy()
+            if kind == "power" and self._output == "amplitude":
+                win = np.square(win)
+            if standardize:
+                mean, std = self.device_moments(square=(kind == "power" and self._output == "amplitude"))
+                win = (win - mean) / std
+            return self._time[time_slice], self._frequencies[freq_slice], win
         data = self.amplitude if kind == "amplitude" else self.power
         if standardize:
             data = (data - data.mean()) / data.std()
         return self._time[time_slice], self._frequencies[freq_slice], data[freq_slice, time_slice]
+
+    def device_moments(self, square=False):
+        """(mean, std) in float64 over the whole device-resident result (of its square when
+        ``square``), reduced on the GPU: the statistics ``plot(standardize=True)`` uses
+        (reference transforms.py:360-366)."""
+        import ctypes as C
+        import torch
+        from .. import _lib
+        if self._result is None:
+            raise ValueError("no device-resident result: call transform(..., keep_on_device=True)")
+        res = self._result
+        if res.is_complex() or not res.is_contiguous():
+            raise ValueError("moments need a contiguous real result")
+        out = (C.c_double * 2)()
+        st = torch.cuda.current_stream(res.device).cuda_stream
+        _lib.check(_lib.load().gcwt_moments(res.data_ptr(), _lib.F32 if res.dtype == torch.float32 else _lib.F64,
+                                            res.numel(), 1 if square else 0, out, self._device, st))
+        return float(out[0]), float(out[1])
 
     def plot(self, *, kind=None, timescale=None, logscale=None, standardize=None, relative_time=None,
              center_time=None, time_limits=None, freq_limits=None, ax=None, **kwargs):

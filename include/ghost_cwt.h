@@ -146,6 +146,12 @@ int gcwt_fastconv(const double *signal, int32_t signal_is_complex, int64_t n,
 int gcwt_dft(const double *x_complex, int64_t n, int32_t sign, double *out_complex, int32_t device);
 int gcwt_analytic_signal(const double *x, int64_t n, double *out_complex, int32_t device);
 
+/* Global mean and (population) standard deviation, in fp64, of n device elements x (or of x^2 when
+ * square != 0: power from an amplitude array).  What plot(standardize=True) computes on the host
+ * over the whole (S, N) array (ghost/wave/transforms.py:360-366).  out_host[0] = mean, [1] = std. */
+int gcwt_moments(const void *x_dev, int32_t type, int64_t n, int32_t square, double *out_host,
+                 int32_t device, void *stream);
+
 /* Bytes of device workspace the plan currently holds (grows on demand in execute). */
 size_t gcwt_plan_workspace_bytes(const gcwt_plan *plan);
 

@@ -289,6 +289,30 @@ def test_analog_signal_array_input():
     assert _maxrel(cwt.amplitude, amp).max() <= FP64_BAR
 
 
+def test_plot_inputs_and_device_standardisation():
+    """The arrays plot() draws (reference transforms.py:356-367): amplitude or power, optional
+    global standardisation, time / frequency windows -- from a device-resident result without a
+    full host copy, against the same selection done with numpy on the oracle's output."""
+    fs, n = 1000.0, 30000
+    x = synth.chirp_pink(n, fs, 12, np.float32)
+    amp, f, _ = orc.cwt_amplitude(x, fs, parallel=True)
+    cwt = ContinuousWaveletTransform(dtype=np.float32)
+    cwt.transform(x, fs=fs, keep_on_device=True)
+    assert cwt.device_result is not None and cwt.device_result.is_cuda
+    for kind, ref in (("amplitude", amp), ("power", amp ** 2)):
+        want = (ref - ref.mean()) / ref.std()
+        mean, std = cwt.device_moments(square=(kind == "power"))
+        assert abs(mean - ref.mean()) <= 1e-5 * abs(ref.mean()) and abs(std - ref.std()) <= 1e-5 * ref.std()
+        t, fr, data = cwt.spectrogram_data(kind=kind, standardize=True, time_limits=[5.0, 12.5], freq_limits=[10.0, 100.0])
+        ts, fsl = slice(5000, 12500), slice(len(f) - np.searchsorted(f[::-1], 100.0), len(f) - np.searchsorted(f[::-1], 10.0))
+        assert data.shape == want[fsl, ts].shape and len(t) == 7500 and np.array_equal(fr, f[fsl])
+        assert np.max(np.abs(data - want[fsl, ts])) <= 2e-4 * np.max(np.abs(want))
+    host = ContinuousWaveletTransform(dtype=np.float32)
+    host.transform(x, fs=fs)
+    _, _, d_host = host.spectrogram_data(kind="power", standardize=True, time_limits=[5.0, 12.5], freq_limits=[10.0, 100.0])
+    assert np.allclose(d_host, data, rtol=0, atol=2e-4 * np.max(np.abs(d_host)))
+
+
 # ------------------------------------------------------------------ time shards (halo semantics)
 @pytest.mark.parametrize("dtype,bar", [(np.float64, 1e-11), (np.float32, 3e-6)])
 def test_time_shards_with_halos_equal_whole(dtype, bar):
