@@ -10,14 +10,25 @@ namespace gcwt {
 constexpr int kBins = 256;          // spectrum bins kept per chunk by the band-limited path
 constexpr int kChunkDec = 1024;     // chunk length in decimated samples (forward FFT size)
 constexpr int kFullN = 4096;        // chunk length of the full-spectrum fused kernel
-constexpr int kMaxClassScales = 16; // scales handled by one fused launch (shared-memory table)
+#ifndef GCWT_MAX_CLASS
+#define GCWT_MAX_CLASS 16
+#endif
+#ifndef GCWT_INTERP_T
+#define GCWT_INTERP_T 8
+#endif
+#ifndef GCWT_INTERP_CTAS
+#define GCWT_INTERP_CTAS 2
+#endif
+constexpr int kMaxClassScales = GCWT_MAX_CLASS; // scales handled by one fused launch (shared-memory table)
 constexpr int kMinFastLevel = 2;    // P = kChunkDec * 2^level / kBins must be >= 16
-constexpr int kInterpT = 10;        // taps of the polyphase interpolator (amplitude / power output)
+constexpr int kInterpT = GCWT_INTERP_T;        // taps of the polyphase interpolator (amplitude / power output)
 constexpr int kInterpMinLevel = 3;  // interpolated classes: coarse spacing U = 2^(level-1) >= 4
 constexpr int kCoarse = 2048;       // coarse |W|^2 samples per chunk and scale (8 columns x 256)
 constexpr int kWideT = 14;          // taps of the interpolator of the wide-spacing classes (U = D)
 constexpr int kWideMaxLevel = 3;    // levels 2 and 3 use U = D when their bands allow it
 constexpr int kCoarseWide = 1024;   // coarse samples per chunk and scale in those classes (4 columns x 256)
+constexpr double kInterpMinOs = 4.0; // |W|^2 over-sampling guaranteed on the grid U = D/2 (band <= kBins bins)
+constexpr double kWideMinOs = 2.5;   // over-sampling required of a class before it may use U = D
 constexpr int kHalfbandT = 19;      // half-band taps run from -T..T
 constexpr int kHalfbandOdd = (kHalfbandT + 1) / 2;
 
