@@ -2,6 +2,8 @@
 #include "plan.h"
 #include "common.cuh"
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <new>
 
 namespace gcwt {
@@ -13,10 +15,11 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 void count_launch(int n) { g_launches += n; }
 int64_t launches_so_far() { return g_launches; }
 
-int prof_begin(gcwt_plan* p, int kind, cudaStream_t st) {
+int prof_begin(gcwt_plan* p, int kind, cudaStream_t st, int tag) {
     if (!p->profile) return -1;
     gcwt_plan::Span sp;
     sp.kind = kind;
+    sp.tag = tag;
     sp.launches = (int)g_launches;
     if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return -1;
     cudaEventRecord(sp.a, st);
@@ -36,6 +39,7 @@ static void prof_collect(gcwt_plan* p) {
         float ms = 0.f;
         if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
             p->prof_ms[sp.kind] += ms;
+            p->class_ms[sp.tag & 63] += ms;
             p->prof_launches[sp.kind] += sp.launches;
         }
         cudaEventDestroy(sp.a);
@@ -191,6 +195,11 @@ int gcwt_profile_read(gcwt_plan* p, double* ms_out, int64_t* launches_out, int32
     if (!p || !ms_out || !launches_out) { set_error("profile_read: NULL argument"); return GCWT_ERR_ARG; }
     cudaSetDevice(p->device);
     prof_collect(p);
+    if (getenv("GCWT_CLASS_TIMES")) {                  // developer aid: per-class milliseconds since the last reset
+        for (int t = 0; t < 64; ++t)
+            if (p->class_ms[t] > 0) fprintf(stderr, "gcwt class level %d: %.4f ms\n", t - 2, p->class_ms[t]);
+    }
+    if (reset) for (int t = 0; t < 64; ++t) p->class_ms[t] = 0;
     for (int k = 0; k < GCWT_PROFILE_KINDS; ++k) {
         ms_out[k] = p->prof_ms[k];
         launches_out[k] = p->prof_launches[k];

@@ -16,15 +16,19 @@ constexpr int kFullN = 4096;        // chunk length of the full-spectrum fused k
 #ifndef GCWT_INTERP_T
 #define GCWT_INTERP_T 8
 #endif
+#ifndef GCWT_WIDE_T
+#define GCWT_WIDE_T 12
+#endif
 #ifndef GCWT_INTERP_CTAS
 #define GCWT_INTERP_CTAS 2
 #endif
 constexpr int kMaxClassScales = GCWT_MAX_CLASS; // scales handled by one fused launch (shared-memory table)
+constexpr int kHalfLevel = 1;     // reported level of full-rate scales computed on the half-rate power grid
 constexpr int kMinFastLevel = 2;    // P = kChunkDec * 2^level / kBins must be >= 16
 constexpr int kInterpT = GCWT_INTERP_T;        // taps of the polyphase interpolator (amplitude / power output)
 constexpr int kInterpMinLevel = 3;  // interpolated classes: coarse spacing U = 2^(level-1) >= 4
 constexpr int kCoarse = 2048;       // coarse |W|^2 samples per chunk and scale (8 columns x 256)
-constexpr int kWideT = 14;          // taps of the interpolator of the wide-spacing classes (U = D)
+constexpr int kWideT = GCWT_WIDE_T;          // taps of the interpolator of the wide-spacing classes (U = D)
 constexpr int kWideMaxLevel = 3;    // levels 2 and 3 use U = D when their bands allow it
 constexpr int kCoarseWide = 1024;   // coarse samples per chunk and scale in those classes (4 columns x 256)
 constexpr double kInterpMinOs = 4.0; // |W|^2 over-sampling guaranteed on the grid U = D/2 (band <= kBins bins)
@@ -55,6 +59,7 @@ struct FastClass {
     // then a kInterpT-tap polyphase interpolator; d_coef is float [U][kInterpT]
     std::vector<int> scale_nmu;     // full-spectrum kernel: occupied 256-bin blocks per scale (2, 4, 8, 16)
     int32_t* d_scale_nmu = nullptr;
+    bool half = false;              // full-rate input, |W|^2 at the even samples, 2x interpolation (level 1)
     bool interp = false;
     bool wide = false;              // coarse spacing U = D (4 columns), kWideT taps; else U = D/2, kInterpT taps
     int log2u = 0;
@@ -85,9 +90,10 @@ struct gcwt_plan {
     double halfband_odd[gcwt::kHalfbandOdd];  // h[1], h[3], ... (h[0] = 0.5)
     gcwt::Workspace ws;
     bool profile = false;
-    struct Span { cudaEvent_t a, b; int kind; int launches; };
+    struct Span { cudaEvent_t a, b; int kind; int launches; int tag; };
     std::vector<Span> spans;
     double prof_ms[GCWT_PROFILE_KINDS] = {0, 0, 0, 0, 0};
+    double class_ms[64] = {0};              // per scale class (level + 2), printed when GCWT_CLASS_TIMES is set
     int64_t prof_launches[GCWT_PROFILE_KINDS] = {0, 0, 0, 0, 0};
     float2* d_twiddle = nullptr;            // e^{-2 pi i k / 4096}, k < 4096 (forward FFTs of the fused kernels)
     double* d_means = nullptr;              // internal per-channel means
@@ -101,7 +107,7 @@ int ensure_workspace(gcwt_plan* p, size_t bytes);
 void count_launch(int n = 1);
 int64_t launches_so_far();
 // RAII-less profiling span: begin returns an index (or -1 when profiling is off)
-int prof_begin(gcwt_plan* p, int kind, cudaStream_t st);
+int prof_begin(gcwt_plan* p, int kind, cudaStream_t st, int tag = 0);
 void prof_end(gcwt_plan* p, int idx, cudaStream_t st);
 
 // path drivers (each returns a GCWT_* code)

@@ -9,7 +9,10 @@ import torch
 sys.path.insert(0, ".")
 from ghost_b200 import ContinuousWaveletTransform, Morse
 
+import os
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+only = os.environ.get("FUZZ_ONLY")                              # comma-separated case numbers to run (RNG still advances)
+only = set(int(v) for v in only.split(",")) if only else None
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 worst = 0.0
 fails = []
@@ -32,13 +35,17 @@ for case in range(n_cases):
         kw["timestamps"] = ts
     if rng.random() < 0.5:
         kw["freq_limits"] = [fs / 2000.0, fs / 2.5]
+    if only is not None and case not in only:
+        continue
     res = {}
+    lev = np.zeros(0, dtype=np.int32)
     try:
         for dt in (np.float64, np.float32):
             cwt = ContinuousWaveletTransform(wavelet=Morse(gamma=gamma, beta=beta), dtype=dt, output=output)
             cwt.transform(x, **kw)
             res[dt] = cwt.coefficients if output == "complex" else (cwt.amplitude if output == "amplitude" else cwt.power)
-            lev = cwt.last_plan.levels()
+            if cwt.last_plan is not None:
+                lev = cwt.last_plan.levels()
     except Exception as e:                                      # noqa: BLE001
         fails.append((case, gamma, beta, fs, n, nch, vpo, output, repr(e)))
         print("case %d EXC %r" % (case, e), flush=True)
@@ -48,7 +55,9 @@ for case in range(n_cases):
         print("case %d: no scales (n=%d)" % (case, n)); continue
     num = np.linalg.norm((a - b).reshape(a.shape[0], a.shape[1], -1), axis=2)
     den = np.linalg.norm(b.reshape(b.shape[0], b.shape[1], -1), axis=2)
-    err = float((num / den).max())
+    rel = num / den
+    err = float(rel.max())
+    ci, si = np.unravel_index(int(np.argmax(rel)), rel.shape)
     bar = 2e-5 if output == "power" else 1e-5
     worst = max(worst, err)
     tag = "ok " if err <= bar else "BAD"
@@ -57,6 +66,10 @@ for case in range(n_cases):
     print("case %2d %s g=%g b=%g fs=%g n=%d ch=%d vpo=%d %s epochs=%d S=%d levels=%s err=%.2e" % (
         case, tag, gamma, beta, fs, n, nch, vpo, output, 2 if ts is not None else 1, a.shape[1],
         sorted(set(lev.tolist())), err), flush=True)
+    if err > 0.5 * bar:
+        order = np.argsort(rel.max(axis=0))[::-1][:6]
+        print("      worst scales (index, level, L, err): " + ", ".join(
+            "(%d, %d, %.2e)" % (int(i), int(lev[i]) if len(lev) else 99, float(rel[:, i].max())) for i in order), flush=True)
 print("worst %.2e, failures %d" % (worst, len(fails)))
 for f in fails:
     print("FAIL", f)
