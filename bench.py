@@ -282,8 +282,7 @@ def run_ours(args):
     interp_on = wl["output"] != "complex"
     # level 2 joins the interpolated classes when its bands allow the wide coarse grid (no direct launches then)
     min_interp_level = 2 if prof["fused_banded"][1] == 0 else 3
-    # level 1 = full-rate input on the half-rate power grid (fused_half_kernel), also an interpolated class
-    n_interp = int(((levels >= min_interp_level) | (levels == 1)).sum()) if interp_on else 0
+    n_interp = int((levels >= min_interp_level).sum()) if interp_on else 0
     n_banded = int((levels >= 0).sum()) - n_interp
     n_full = int((levels == -1).sum())
     fam_scales = {"fused_interp": n_interp, "fused_banded": n_banded, "fused_full": n_full}

@@ -38,8 +38,6 @@ __constant__ float c_interp_small[kSmallCoef];
 // wide-spacing classes: U = 4 (level 2) and U = 8 (level 3), kWideT taps
 constexpr int kWideCoef = (4 + 8) * kWideT;
 __constant__ float c_interp_wide[kWideCoef];
-// half-rate classes (U = 2): the half-sample phase is symmetric, kWideT / 2 distinct taps
-__constant__ float c_interp_half[kWideT / 2];
 
 // ============================================================================ planner
 static double bessel_i0(double x) {
@@ -158,19 +156,6 @@ static int band_width_bins(const gcwt_plan* p, const PlanResponses& pr, int s, i
     return hi - lo + 1;
 }
 
-// Same on the 4096-point grid of the full-rate kernels.
-static int band_width_full(const gcwt_plan* p, const PlanResponses& pr, int s) {
-    const double* g = pr.full(s);
-    const double e_tot = filter_energy(p, p->scales[s], kFullN);
-    const double budget = 0.5 * p->band_tol * p->band_tol * e_tot;
-    int lo = 0, hi = kFullN - 1;
-    double acc = 0.0;
-    while (lo < hi && acc + g[lo] * g[lo] < budget) { acc += g[lo] * g[lo]; ++lo; }
-    acc = 0.0;
-    while (hi > lo && acc + g[hi] * g[hi] < budget) { acc += g[hi] * g[hi]; --hi; }
-    return hi - lo + 1;
-}
-
 static int choose_level(const gcwt_plan* p, const PlanResponses& pr, int s) {
     const ScaleInfo& sc = p->scales[s];
     if (!(p->flags & GCWT_FLAG_FORCE_GENERIC)) {
@@ -185,7 +170,7 @@ static int choose_level(const gcwt_plan* p, const PlanResponses& pr, int s) {
 }
 
 static void class_geometry(FastClass& fc) {
-    const int64_t d = (fc.level >= 0 && !fc.half) ? (int64_t(1) << fc.level) : 1;
+    const int64_t d = fc.level >= 0 ? (int64_t(1) << fc.level) : 1;
     const int64_t align = std::max<int64_t>(d, 16);
     // interpolated classes read kInterpT coarse samples around every output: keep them valid
     const int taps = fc.wide ? kWideT : kInterpT;
@@ -259,10 +244,6 @@ static int upload_constants(const gcwt_plan* p) {
         all.insert(all.end(), part.begin(), part.end());
     }
     GCWT_CUDA_OK(cudaMemcpyToSymbol(c_interp_wide, all.data(), sizeof(float) * kWideCoef));
-    design_interpolator(1, part, kWideT, kWideMinOs);              // phase 1 of U = 2: c[t] == c[T - 1 - t]
-    float half[kWideT / 2];
-    for (int t = 0; t < kWideT / 2; ++t) half[t] = 0.5f * (part[kWideT + t] + part[2 * kWideT - 1 - t]);
-    GCWT_CUDA_OK(cudaMemcpyToSymbol(c_interp_half, half, sizeof(half)));
     return GCWT_OK;
 }
 
@@ -291,25 +272,18 @@ int fast_plan_build(gcwt_plan* p) {
     for (int s = 0; s < p->n_scales; ++s) {
         ScaleInfo& sc = p->scales[s];
         sc.level = choose_level(p, pr, s);
-        // full-rate scales that live in the first two 256-bin blocks and whose |W|^2 stays
-        // kWideMinOs over-sampled at spacing 2 (coarse Nyquist pi/2 = 1024 bins): "level 1"
-        if (sc.level == -1 && p->out_kind != GCWT_OUT_COMPLEX && !(p->flags & GCWT_FLAG_NO_INTERP) &&
-            full_extent(p, pr, s) == 2 && 1024.0 / (double)band_width_full(p, pr, s) >= kWideMinOs)
-            sc.level = kHalfLevel;
         if (sc.level == -2) p->generic_ids.push_back(s);
         else by_level[sc.level].push_back(s);
-        if (sc.level != kHalfLevel) p->max_level = std::max(p->max_level, sc.level);   // pyramid depth
+        p->max_level = std::max(p->max_level, sc.level);
     }
     for (auto& kv : by_level) {
         const int level = kv.first;
         const std::vector<int>& ids = kv.second;
-        const bool half = level == kHalfLevel;
-        const int cap = (level >= 0 && !half) ? kMaxClassScales : kMaxFullScales;
+        const int cap = level >= 0 ? kMaxClassScales : kMaxFullScales;
         for (size_t i0 = 0; i0 < ids.size(); i0 += cap) {
             FastClass fc;
             fc.level = level;
-            fc.half = half;
-            fc.nc_full = (level >= 0 && !half) ? ((int64_t)kChunkDec << level) : kFullN;
+            fc.nc_full = level >= 0 ? ((int64_t)kChunkDec << level) : kFullN;
             fc.scale_ids.assign(ids.begin() + i0, ids.begin() + std::min(ids.size(), i0 + cap));
             fc.lmax = 1;
             for (int id : fc.scale_ids) fc.lmax = std::max(fc.lmax, p->scales[id].L);
@@ -319,24 +293,23 @@ int fast_plan_build(gcwt_plan* p) {
             // |W|^2 of a scale whose filter spans w bins of the (1024 D)-point grid reaches 2 pi w / (1024 D);
             // the coarse Nyquist frequency is pi / U: over-sampling 1024 / w on U = D/2, 512 / w on U = D
             int wmax = 1;
-            if (half) { fc.interp = true; fc.wide = true; fc.log2u = 1; }
-            else if (level >= 0)
+            if (level >= 0)
                 for (int id : fc.scale_ids) wmax = std::max(wmax, band_width_bins(p, pr, id, level));
-            if (may_interp && !half && level >= 2 && level <= kWideMaxLevel) {
+            if (may_interp && level >= 2 && level <= kWideMaxLevel) {
                 // coarse spacing U = D is allowed when |W|^2 stays 2.5x over-sampled on that grid
                 if (512.0 / (double)wmax >= kWideMinOs) { fc.interp = true; fc.wide = true; fc.log2u = level; }
             }
             class_geometry(fc);
             if (fc.hop <= 0) { set_error("planner: non-positive hop"); return GCWT_ERR_ARG; }
-            const int nb = half ? 2 * kBins : (level >= 0 ? kBins : kFullN);
+            const int nb = level >= 0 ? kBins : kFullN;
             const int ns = (int)fc.scale_ids.size();
             std::vector<float2> tab((size_t)ns * nb);
             for (int i = 0; i < ns; ++i) {
                 const ScaleInfo& sc = p->scales[fc.scale_ids[i]];
-                const double* gsrc = (level >= 0 && !half) ? pr.level(fc.scale_ids[i], level) : pr.full(fc.scale_ids[i]);
+                const double* gsrc = level >= 0 ? pr.level(fc.scale_ids[i], level) : pr.full(fc.scale_ids[i]);
                 for (int m = 0; m < nb; ++m) {
                     double g = gsrc[m];
-                    if (level >= 0 && !half) {
+                    if (level >= 0) {
                         for (int j = 1; j <= level; ++j) g /= hb[(size_t)j * kBins + m];
                         g /= (double)kChunkDec;
                     } else {
@@ -353,7 +326,7 @@ int fast_plan_build(gcwt_plan* p) {
             }
             GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_table, sizeof(float2) * tab.size()));
             GCWT_CUDA_OK(cudaMemcpy(fc.d_table, tab.data(), sizeof(float2) * tab.size(), cudaMemcpyHostToDevice));
-            if (fc.interp && !half) {
+            if (fc.interp) {
                 std::vector<float> coef;
                 // per-class taps (spacings U >= 16): fitted to the band this class really occupies
                 if (fc.wide) {
@@ -1037,8 +1010,10 @@ fused_full_kernel(const FusedParams prm) {
     for (int s = 0; s < prm.n_scales; ++s) {
         float2 a[16];
         const int nmu = s_nmu[s];
-        // the table rows stream from L2 through L1: this kernel is co-limited by the LSU data pipe,
-        // and staging them through shared memory (cp.async) costs a second LSU operation per entry
+        // the table rows stream from L2 through L1: this kernel is co-limited by the LSU data pipe and
+        // the issue slots, not by this latency -- staging the rows ahead of time changed nothing
+        // measurable, neither with cp.async (a second LSU operation per entry) nor with a TMA bulk
+        // copy + mbarrier one scale ahead (8.89 vs 8.92 ms on config 2)
         const float2* tab = prm.table + (int64_t)s * kFullN + tid;
         if (nmu == 2) full_prepass<2>(Yf, tab, A, tw4k);
         else if (nmu == 4) full_prepass<4>(Yf, tab, A, tw4k);
@@ -1062,153 +1037,6 @@ fused_full_kernel(const FusedParams prm) {
         // no trailing barrier: the next scale's pre-pass writes A, whose readers all passed
         // the second barrier above; its pass 1 writes ex only after the next first barrier,
         // which every thread reaches after finishing the reads of ex just done.
-    }
-}
-
-// ---------------------------------------------------------------------------- half-rate power
-// Amplitude / power of full-rate scales whose filters live in the first two 256-bin blocks of the
-// 4096-point grid (below pi/4) and whose |W|^2 is at least kWideMinOs over-sampled at spacing 2:
-// W is needed at the even samples only, a 2048-point inverse transform with 512 non-zero bins =
-// 8 columns of 256-point transforms (two scales per 16-lane pass instead of one), and the odd
-// samples of |W|^2 come from the symmetric kWideT-tap half-sample interpolator.  The 512 useful
-// spectrum bins stay in registers (two per thread), so the kernel needs two shared buffers only.
-// smem: B0[4096 + 256] (forward result, then exchange) | B1[4096] (chunk, then aliases / coarse rows)
-constexpr size_t kHalfSmem = sizeof(float2) * (2 * kFullN + 256) + sizeof(int) * kMaxFullScales;
-static_assert(kWideT % 4 == 0, "half-rate interpolator reads its window as aligned 64-bit pairs");
-constexpr int kPcStrideH = kFullN / 2 + 16;       // % 32 == 16: the two scales of a pass hit different banks
-
-template <int KIND>
-__device__ __forceinline__ void interp_rows_half(const float* __restrict__ pc, float* __restrict__ row,
-                                                 int own_lo, int own_hi, bool aligned) {
-    constexpr int HT = kWideT / 2;
-    // thread <-> two coarse intervals = four consecutive outputs (one 128-bit store, contiguous
-    // across lanes); their T + 1 coarse samples arrive as 64-bit shared-memory loads
-    for (int j = (own_lo >> 2) + (int)threadIdx.x; 4 * j < own_hi; j += 256) {
-        const int i0 = 2 * j;                                     // even coarse index: outputs 4j .. 4j+3
-        float w[kWideT + 2];
-#pragma unroll
-        for (int v = 0; v < (kWideT + 2) / 2; ++v) {
-            const float2 t = *(const float2*)(pc + i0 - HT + 2 * v);
-            w[2 * v] = t.x; w[2 * v + 1] = t.y;
-        }
-        // w[k] = p[i0 - HT + k]; interval i0 interpolates p[i0 - HT + 1 .. i0 + HT], i0 + 1 one further
-        float o[4];
-        o[0] = w[HT]; o[2] = w[HT + 1];
-        float acc0 = c_interp_half[0] * (w[1] + w[kWideT]);
-        float acc1 = c_interp_half[0] * (w[2] + w[kWideT + 1]);
-#pragma unroll
-        for (int t = 1; t < HT; ++t) {
-            acc0 = fmaf(c_interp_half[t], w[1 + t] + w[kWideT - t], acc0);
-            acc1 = fmaf(c_interp_half[t], w[2 + t] + w[kWideT + 1 - t], acc1);
-        }
-        o[1] = acc0; o[3] = acc1;
-        if (KIND == GCWT_OUT_AMPLITUDE) {
-            o[0] = sqrt_approx(o[0]); o[2] = sqrt_approx(o[2]);
-            o[1] = sqrt_abs_approx(o[1]); o[3] = sqrt_abs_approx(o[3]);
-        } else {
-            o[1] = fmaxf(o[1], 0.f); o[3] = fmaxf(o[3], 0.f);
-        }
-        float* op = row + 4 * j;
-        if (aligned && 4 * j + 4 <= own_hi) *(float4*)op = make_float4(o[0], o[1], o[2], o[3]);
-        else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (4 * j + e < own_hi) op[e] = o[e];
-        }
-    }
-}
-
-template <typename TIn, int KIND>
-__global__ void __launch_bounds__(256, 2)
-fused_half_kernel(const FusedParams prm) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* B0 = (float2*)smem_raw;
-    float2* B1 = B0 + kFullN + 256;
-    int* s_ids = (int*)(B1 + kFullN);
-
-    const int tid = threadIdx.x;
-    const int r = tid & 15;
-    const int g = tid >> 4;
-    const int64_t q = blockIdx.x % prm.n_chunks;
-    const int64_t c = blockIdx.x / prm.n_chunks;
-    const int64_t t0 = q * prm.hop - prm.offset;
-
-    float2 y0, y1;                                                 // spectrum bins tid and tid + 256
-    {
-        const TIn* src = (const TIn*)prm.src + c * prm.src_stride;
-        const double mu = prm.means[c];
-        TIn raw[kFullN / 256];
-        unsigned inside = 0;
-#pragma unroll
-        for (int k = 0; k < kFullN / 256; ++k) {
-            const int64_t u = t0 + tid + 256 * k;
-            const bool ok = u >= prm.src_lo && u < prm.src_hi;
-            raw[k] = ok ? src[u] : (TIn)0;
-            inside |= (unsigned)ok << k;
-        }
-#pragma unroll
-        for (int k = 0; k < kFullN / 256; ++k)
-            B1[tid + 256 * k] = make_float2((inside >> k & 1) ? (float)((double)raw[k] - mu) : 0.f, 0.f);
-        if (tid < prm.n_scales) s_ids[tid] = prm.scale_ids[tid];
-        __syncthreads();
-        smem_fft4096_forward(B1, B0, prm.twf);
-        y0 = B0[tid];
-        y1 = B0[tid + 256];
-    }
-    float2 tw[16], tw2k[8];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) tw[k] = tw_pos(prm.twf, 16 * g * k);          // e^{2 pi i g k / 256}
-#pragma unroll
-    for (int k = 0; k < 8; ++k) tw2k[k] = tw_pos(prm.twf, 2 * tid * k);        // e^{2 pi i m' k / 2048}
-    const int own_lo = (int)prm.offset;
-    const int own_hi = (int)min(prm.offset + prm.hop, prm.n - t0);
-    float* const out_c = (float*)prm.out + c * prm.c_stride + t0;
-    const bool aligned = prm.iters != 0;
-    float2* const A = B1;
-    float2* const ex = B0;
-    float* const Pc = (float*)B1;
-    const int col = r & 7, sidx = r >> 3;
-    __syncthreads();                                               // spectrum is in registers: B0 is free
-    for (int pair = 0; pair < prm.n_scales; pair += 2) {
-        // aliases: bins m' and m' + 256 folded onto the 8 even columns, both scales of the pass
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-            const int s = min(pair + sl, prm.n_scales - 1);
-            const float2* tab = prm.table + (int64_t)s * (2 * kBins) + tid;
-            const float2 z0 = cmul(y0, __ldg(tab));
-            const float2 z1 = cmul(y1, __ldg(tab + kBins));
-            const float h = 0.70710678118654752440f;
-            const float2 zr = make_float2((z1.x - z1.y) * h, (z1.x + z1.y) * h);   // z1 e^{i pi/4}
-            float2 v[8];
-            v[0] = cadd(z0, z1);            v[4] = csub(z0, z1);
-            v[2] = cadd(z0, mul_i<+1>(z1)); v[6] = csub(z0, mul_i<+1>(z1));
-            v[1] = cadd(z0, zr);            v[5] = csub(z0, zr);
-            v[3] = cadd(z0, mul_i<+1>(zr)); v[7] = csub(z0, mul_i<+1>(zr));
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                A[tid * 16 + ((sl * 8 + k) ^ (tid & 15))] = k ? cmul(v[k], tw2k[k]) : v[k];
-        }
-        __syncthreads();
-        float2 a[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 16 + (r ^ g)];
-        dft16<+1>(a);
-        float2* e = ex + (g * 16) * 16 + r;
-        e[0] = a[0];
-#pragma unroll
-        for (int k = 1; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
-        __syncthreads();                                           // all reads of A are done: Pc may overwrite it
-        const float2* e2 = ex + g * 16 + r;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
-        dft16<+1>(a);
-        float* pc = Pc + sidx * kPcStrideH + g * 8 + col;          // coarse index (g + 16 k) * 8 + col
-#pragma unroll
-        for (int k = 0; k < 16; ++k) pc[k * 128] = a[k].x * a[k].x + a[k].y * a[k].y;
-        __syncthreads();
-        for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl)
-            interp_rows_half<KIND>(Pc + sl * kPcStrideH, out_c + (int64_t)s_ids[pair + sl] * prm.s_stride,
-                                   own_lo, own_hi, aligned);
-        __syncthreads();
     }
 }
 
@@ -1313,7 +1141,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         // the thread <-> interval interpolators (U = 2, 4 and the wide classes) write 128-bit vectors:
         // rows must be 16-byte aligned
         const bool rows_aligned = ((uintptr_t)out % 16 == 0) && (s_stride % 4 == 0) && (c_stride % 4 == 0);
-        if (fc.level >= 0 && !fc.half && fc.interp && ((fc.log2u >= 3 && !fc.wide) || rows_aligned)) {
+        if (fc.level >= 0 && fc.interp && ((fc.log2u >= 3 && !fc.wide) || rows_aligned)) {
             // (an unaligned wide class falls through to the direct kernel with its own geometry)
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1340,16 +1168,6 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
                 fused_interp_kernel<GCWT_OUT_AMPLITUDE, false><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
             else
                 fused_interp_kernel<GCWT_OUT_POWER, false><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
-        } else if (fc.half) {
-            prm.src = x; prm.src_stride = x_stride; prm.src_lo = -halo_l; prm.src_hi = n + halo_r;
-            prm.log2d = 0; prm.p_cols = 8; prm.log2p = 3; prm.units_per_chunk = 1;
-            prm.iters = rows_aligned ? 1 : 0;                      // 128-bit stores allowed
-            const int64_t nblk = n_channels * prm.n_chunks;
-            if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
-            if (p->out_kind == GCWT_OUT_AMPLITUDE)
-                fused_half_kernel<TIn, GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kHalfSmem, st>>>(prm);
-            else
-                fused_half_kernel<TIn, GCWT_OUT_POWER><<<(unsigned)nblk, 256, kHalfSmem, st>>>(prm);
         } else if (fc.level >= 0) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1384,8 +1202,6 @@ static int set_smem_attrs() {
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_half_kernel<TIn, GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_half_kernel<TIn, GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHalfSmem));
     return GCWT_OK;
 }
 

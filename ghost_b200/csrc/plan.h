@@ -23,7 +23,6 @@ constexpr int kFullN = 4096;        // chunk length of the full-spectrum fused k
 #define GCWT_INTERP_CTAS 2
 #endif
 constexpr int kMaxClassScales = GCWT_MAX_CLASS; // scales handled by one fused launch (shared-memory table)
-constexpr int kHalfLevel = 1;     // reported level of full-rate scales computed on the half-rate power grid
 constexpr int kMinFastLevel = 2;    // P = kChunkDec * 2^level / kBins must be >= 16
 constexpr int kInterpT = GCWT_INTERP_T;        // taps of the polyphase interpolator (amplitude / power output)
 constexpr int kInterpMinLevel = 3;  // interpolated classes: coarse spacing U = 2^(level-1) >= 4
@@ -59,7 +58,6 @@ struct FastClass {
     // then a kInterpT-tap polyphase interpolator; d_coef is float [U][kInterpT]
     std::vector<int> scale_nmu;     // full-spectrum kernel: occupied 256-bin blocks per scale (2, 4, 8, 16)
     int32_t* d_scale_nmu = nullptr;
-    bool half = false;              // full-rate input, |W|^2 at the even samples, 2x interpolation (level 1)
     bool interp = false;
     bool wide = false;              // coarse spacing U = D (4 columns), kWideT taps; else U = D/2, kInterpT taps
     int log2u = 0;
