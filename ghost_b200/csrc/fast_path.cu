@@ -364,7 +364,7 @@ void fast_plan_free(gcwt_plan* p) {
 // ============================================================================ pyramid
 // out[i] = 0.5 in[2i] + sum_k h[2k+1] (in[2i-(2k+1)] + in[2i+(2k+1)]), zero outside the
 // readable range of `in`.  Level 1 reads the raw recording and removes the mean.
-constexpr int kPyrTile = 512;   // outputs per block
+constexpr int kPyrTile = 1024;  // outputs per block: four consecutive outputs per thread
 
 template <typename TIn, bool FIRST>
 __global__ void __launch_bounds__(256)
@@ -372,11 +372,17 @@ pyramid_kernel(const TIn* __restrict__ in, int64_t in_stride, int64_t in_lo, int
                const double* __restrict__ means, float* __restrict__ out, int64_t out_stride,
                int64_t out_lo, int64_t out_len) {
     // The tile of 2*kPyrTile + 2T inputs is kept de-interleaved: ev[i] = input(u0 + 2i),
-    // od[i] = input(u0 + 2i + 1).  With T odd every tap of output j reads ev[j + const] and the
-    // centre reads od[j + const]: consecutive lanes hit consecutive banks (no conflicts).
-    constexpr int kHalf = kPyrTile + kHalfbandT + 1;
-    __shared__ float ev[kHalf];
-    __shared__ float od[kHalf];
+    // od[i] = input(u0 + 2i + 1), u0 = 2 i0 - T.  With T odd the centre of output j is od[j + kMid]
+    // and its taps are ev[j + kMid - k], ev[j + kMid + 1 + k].  A thread owns outputs 4 tid .. 4 tid + 3:
+    // with kMid = 9 its 23 even-phase inputs start at ev[4 tid] and its four centres at od[4 tid + 9],
+    // so everything arrives as 128-bit shared-memory loads (od is stored shifted by kMid + 3 to line
+    // up) -- 7 loads per 4 outputs instead of 21 per output -- and leaves as one 128-bit store.
+    static_assert(kHalfbandT == 19, "tile indexing below assumes kMid == 9");
+    constexpr int kMid = (kHalfbandT - 1) / 2;
+    constexpr int kEv = kPyrTile + 2 * kMid + 2 + 4;                // 4 tid + 23 <= kEv
+    constexpr int kOdShift = 12 - kMid;                             // od[i] lives at ods[i + kOdShift]: centre 4 tid + 12
+    __shared__ __align__(16) float ev[kEv];
+    __shared__ __align__(16) float ods[kEv + 16];
     const int c = blockIdx.y;
     const int64_t i0 = out_lo + (int64_t)blockIdx.x * kPyrTile;     // first output index of the block
     const int64_t u0 = 2 * i0 - kHalfbandT;                         // first input index needed
@@ -386,22 +392,31 @@ pyramid_kernel(const TIn* __restrict__ in, int64_t in_stride, int64_t in_lo, int
         const int64_t u = u0 + k;
         float v = 0.f;
         if (u >= in_lo && u < in_hi) v = FIRST ? (float)((double)src[u] - mu) : (float)src[u];
-        if (k & 1) od[k >> 1] = v; else ev[k >> 1] = v;
+        if (k & 1) ods[(k >> 1) + kOdShift] = v; else ev[k >> 1] = v;
     }
     __syncthreads();
-    constexpr int kMid = (kHalfbandT - 1) / 2;                      // centre sample 2j + T = od[j + kMid]
-    for (int j = threadIdx.x; j < kPyrTile; j += blockDim.x) {
-        const int64_t i = i0 + j;
-        if (i - out_lo >= out_len) break;
-        // tap t = 2k+1 reads inputs 2j + T -+ t = ev[j + (T -+ t) / 2]
+    const int j0 = 4 * threadIdx.x;
+    if (i0 + j0 - out_lo >= out_len) return;
+    float e[24];
+#pragma unroll
+    for (int v = 0; v < 6; ++v) {
+        const float4 t = *(const float4*)(ev + j0 + 4 * v);
+        e[4 * v] = t.x; e[4 * v + 1] = t.y; e[4 * v + 2] = t.z; e[4 * v + 3] = t.w;
+    }
+    const float4 ctr = *(const float4*)(ods + j0 + 12);              // od[j0 + kMid .. + 3]
+    const float cv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
         // fp32 accumulation, smallest taps first (fp64 would spend the kernel on conversions)
         float acc = 0.f;
 #pragma unroll
         for (int k = kHalfbandOdd - 1; k >= 0; --k)
-            acc = fmaf(c_halfband[k], ev[j + kMid - k] + ev[j + kMid + 1 + k], acc);
-        acc = fmaf(0.5f, od[j + kMid], acc);
-        out[(int64_t)c * out_stride + (i - out_lo)] = acc;
+            acc = fmaf(c_halfband[k], e[q + kMid - k] + e[q + kMid + 1 + k], acc);
+        o[q] = fmaf(0.5f, cv[q], acc);
     }
+    // rows are padded to a multiple of four floats: the last quad may spill into the padding
+    *(float4*)(out + (int64_t)c * out_stride + (i0 + j0 - out_lo)) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // ============================================================================ fused kernels
