@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <type_traits>
 
 namespace gcwt {
 
@@ -387,12 +388,25 @@ pyramid_kernel(const TIn* __restrict__ in, int64_t in_stride, int64_t in_lo, int
     const int64_t i0 = out_lo + (int64_t)blockIdx.x * kPyrTile;     // first output index of the block
     const int64_t u0 = 2 * i0 - kHalfbandT;                         // first input index needed
     const TIn* src = in + (int64_t)c * in_stride - (FIRST ? 0 : in_lo);   // level arrays start at in_lo
-    const double mu = FIRST ? means[c] : 0.0;
-    for (int k = threadIdx.x; k < 2 * kPyrTile + 2 * kHalfbandT; k += blockDim.x) {
+    // fp32 recordings: the mean is subtracted in fp32 (the rounding of the mean itself, <= 6e-8 |mean|,
+    // is a constant offset the zero-DC filters ignore); fp64 recordings keep the fp64 subtraction
+    typedef typename std::conditional<std::is_same<TIn, float>::value, float, double>::type TSub;
+    const TSub mu = FIRST ? (TSub)means[c] : (TSub)0;
+    constexpr int kIn = 2 * kPyrTile + 2 * kHalfbandT;              // inputs per tile
+    constexpr int kRounds = (kIn + 255) / 256;
+    TIn raw[kRounds];
+#pragma unroll
+    for (int it = 0; it < kRounds; ++it) {                           // all loads of the tile in flight at once
+        const int k = (int)threadIdx.x + 256 * it;
         const int64_t u = u0 + k;
-        float v = 0.f;
-        if (u >= in_lo && u < in_hi) v = FIRST ? (float)((double)src[u] - mu) : (float)src[u];
-        if (k & 1) ods[(k >> 1) + kOdShift] = v; else ev[k >> 1] = v;
+        raw[it] = (k < kIn && u >= in_lo && u < in_hi) ? src[u] : (TIn)0;
+    }
+#pragma unroll
+    for (int it = 0; it < kRounds; ++it) {
+        const int k = (int)threadIdx.x + 256 * it;
+        const int64_t u = u0 + k;
+        const float v = (u >= in_lo && u < in_hi) ? (FIRST ? (float)((TSub)raw[it] - mu) : (float)raw[it]) : 0.f;
+        if (k < kIn) { if (k & 1) ods[(k >> 1) + kOdShift] = v; else ev[k >> 1] = v; }
     }
     __syncthreads();
     const int j0 = 4 * threadIdx.x;
@@ -720,16 +734,16 @@ __device__ __forceinline__ void interp_rows(const float* __restrict__ pc, float*
             }
             op += (int64_t)T << lu;
         }
-        if (base < b_t) {                                         // tail group
+        // tail: fewer than T intervals, leave as soon as they are done (the lanes of a warp share
+        // the count except in the recording's last chunk, so the exit rarely diverges)
 #pragma unroll
-            for (int u = 0; u < T; ++u) {
-                w[(u + T - 1) % T] = pc[base + u + T / 2];
-                float acc = c[0] * w[u % T];
+        for (int u = 0; u < T; ++u) {
+            if (base + u >= b_t) break;
+            w[(u + T - 1) % T] = pc[base + u + T / 2];
+            float acc = c[0] * w[u % T];
 #pragma unroll
-                for (int j = 1; j < T; ++j) acc = fmaf(c[j], w[(u + j) % T], acc);
-                acc = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_abs_approx(acc) : fmaxf(acc, 0.f);
-                st_pred(op + ((int64_t)u << lu), acc, (unsigned)(base + u < b_t));
-            }
+            for (int j = 1; j < T; ++j) acc = fmaf(c[j], w[(u + j) % T], acc);
+            op[(int64_t)u << lu] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_abs_approx(acc) : fmaxf(acc, 0.f);
         }
     }
 }
@@ -742,28 +756,10 @@ __device__ __forceinline__ void interp_rows_small(const float* __restrict__ pc, 
                                                   int ia, int ib, int own_hi) {
     constexpr int U = 1 << LU;
     constexpr int COFF = (LU == 1) ? 0 : (LU == 2 ? 2 * kInterpT : 6 * kInterpT);
-#ifdef GCWT_PREFETCH
-    float wn[kInterpT];
-    {
-        const int i0 = min(ia + (int)threadIdx.x, ib - 1);
-#pragma unroll
-        for (int j = 0; j < kInterpT; ++j) wn[j] = pc[i0 - (kInterpT / 2 - 1) + j];
-    }
-#endif
     for (int iota = ia + (int)threadIdx.x; iota < ib; iota += 256) {
         float w[kInterpT];
-#ifdef GCWT_PREFETCH
-#pragma unroll
-        for (int j = 0; j < kInterpT; ++j) w[j] = wn[j];
-        {
-            const int i1 = min(iota + 256, ib - 1);               // next iteration's window, in flight during the FMAs
-#pragma unroll
-            for (int j = 0; j < kInterpT; ++j) wn[j] = pc[i1 - (kInterpT / 2 - 1) + j];
-        }
-#else
 #pragma unroll
         for (int j = 0; j < kInterpT; ++j) w[j] = pc[iota - (kInterpT / 2 - 1) + j];
-#endif
         float o[U];
         o[0] = w[kInterpT / 2 - 1];                               // phase 0 sits on a coarse sample
 #pragma unroll
@@ -795,28 +791,10 @@ __device__ __forceinline__ void interp_rows_wide(const float* __restrict__ pc, f
                                                  int ia, int ib, int own_hi) {
     constexpr int U = 1 << LU;
     constexpr int COFF = (LU == 2) ? 0 : 4 * kWideT;
-#ifdef GCWT_PREFETCH
-    float wn[kWideT];
-    {
-        const int i0 = min(ia + (int)threadIdx.x, ib - 1);
-#pragma unroll
-        for (int j = 0; j < kWideT; ++j) wn[j] = pc[i0 - (kWideT / 2 - 1) + j];
-    }
-#endif
     for (int iota = ia + (int)threadIdx.x; iota < ib; iota += 256) {
         float w[kWideT];
-#ifdef GCWT_PREFETCH
-#pragma unroll
-        for (int j = 0; j < kWideT; ++j) w[j] = wn[j];
-        {
-            const int i1 = min(iota + 256, ib - 1);               // next iteration's window, in flight during the FMAs
-#pragma unroll
-            for (int j = 0; j < kWideT; ++j) wn[j] = pc[i1 - (kWideT / 2 - 1) + j];
-        }
-#else
 #pragma unroll
         for (int j = 0; j < kWideT; ++j) w[j] = pc[iota - (kWideT / 2 - 1) + j];
-#endif
         float o[U];
         o[0] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_approx(w[kWideT / 2 - 1]) : w[kWideT / 2 - 1];
 #pragma unroll
@@ -927,16 +905,23 @@ fused_interp_kernel(const FusedParams prm) {
         for (int k = 0; k < 16; ++k) pc[k * 16 * NCOL] = a[k].x * a[k].x + a[k].y * a[k].y;
         __syncthreads();
         // (3) polyphase interpolation + epilogue for the scales of this pass
-        for (int sl = 0; sl < NSC && pair + sl < prm.n_scales; ++sl) {
+        // (dealing the (scale, interval) pairs of a pass to the threads as one flat sequence, to save the
+        // partial last round of 256 per scale, measured slower: whole idle warps cost nothing)
+        const int nsc = min(NSC, prm.n_scales - pair);
+        for (int sl = 0; sl < nsc; ++sl) {
             const float* pcs = Pc + sl * PCS;
             float* row = out_c + (int64_t)s_ids[pair + sl] * prm.s_stride;
             if (WIDE) {
                 // (the sliding-window form measured slower here: 12 taps, 4 or 8 lanes per interval)
                 if (lu == 2) interp_rows_wide<KIND, 2>(pcs, row, ia, ib, own_hi);
                 else interp_rows_wide<KIND, 3>(pcs, row, ia, ib, own_hi);
-            }
-            else if (lu >= 4) {
+            } else if (lu == 2) {
+                interp_rows_small<KIND, 2>(pcs, row, ia, ib, own_hi);
+            } else if (lu == 1) {
+                interp_rows_small<KIND, 1>(pcs, row, ia, ib, own_hi);
+            } else {
                 switch (lu) {
+                    case 3:  interp_rows<KIND, 3, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
                     case 4:  interp_rows<KIND, 4, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
                     case 5:  interp_rows<KIND, 5, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
                     case 6:  interp_rows<KIND, 6, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
@@ -947,9 +932,6 @@ fused_interp_kernel(const FusedParams prm) {
                     default: interp_rows<KIND, 0, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
                 }
             }
-            else if (lu == 3) interp_rows<KIND, 3, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi);
-            else if (lu == 2) interp_rows_small<KIND, 2>(pcs, row, ia, ib, own_hi);
-            else interp_rows_small<KIND, 1>(pcs, row, ia, ib, own_hi);
         }
         __syncthreads();
     }

@@ -22,8 +22,16 @@ __global__ void mean_partial_kernel(const TIn* __restrict__ x, int64_t n, int64_
     const int64_t per = (n + nb - 1) / nb;
     const int64_t lo = (int64_t)blockIdx.x * per;
     const int64_t hi = min(n, lo + per);
-    double acc = 0.0;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += (double)xc[i];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;              // independent chains: four loads in flight
+    int64_t i = lo + threadIdx.x;
+    for (; i + 3 * (int64_t)blockDim.x < hi; i += 4 * (int64_t)blockDim.x) {
+        a0 += (double)xc[i];
+        a1 += (double)xc[i + blockDim.x];
+        a2 += (double)xc[i + 2 * (int64_t)blockDim.x];
+        a3 += (double)xc[i + 3 * (int64_t)blockDim.x];
+    }
+    for (; i < hi; i += blockDim.x) a0 += (double)xc[i];
+    const double acc = (a0 + a1) + (a2 + a3);
     __shared__ double sh[256];
     sh[threadIdx.x] = acc;
     __syncthreads();
@@ -34,13 +42,21 @@ __global__ void mean_partial_kernel(const TIn* __restrict__ x, int64_t n, int64_
     if (threadIdx.x == 0) partial[(int64_t)c * nb + blockIdx.x] = sh[0];
 }
 
-__global__ void mean_final_kernel(const double* __restrict__ partial, int nb, int64_t n,
-                                  double* __restrict__ means, int n_channels) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_channels) return;
+// one block per channel: block-wide fp64 reduction of the channel's partial sums
+__global__ void __launch_bounds__(128)
+mean_final_kernel(const double* __restrict__ partial, int nb, int64_t n,
+                  double* __restrict__ means, int n_channels) {
+    const int c = blockIdx.x;
     double acc = 0.0;
-    for (int i = 0; i < nb; ++i) acc += partial[(int64_t)c * nb + i];
-    means[c] = acc / (double)n;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += partial[(int64_t)c * nb + i];
+    __shared__ double sh[128];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) means[c] = sh[0] / (double)n;
 }
 
 int means_blocks(int64_t n_samples) {
@@ -59,8 +75,7 @@ int means_launch(const void* x, int in_type, int64_t n_channels, int64_t n_sampl
         mean_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, n_samples, x_stride, partial);
     else
         mean_partial_kernel<double><<<grid, 256, 0, st>>>((const double*)x, n_samples, x_stride, partial);
-    mean_final_kernel<<<(unsigned)((n_channels + 127) / 128), 128, 0, st>>>(partial, nb, n_samples, d_means,
-                                                                            (int)n_channels);
+    mean_final_kernel<<<(unsigned)n_channels, 128, 0, st>>>(partial, nb, n_samples, d_means, (int)n_channels);
     count_launch(2);
     GCWT_CUDA_OK(cudaGetLastError());
     return GCWT_OK;
