@@ -22,7 +22,7 @@ EXPORTS = (
     "gcwt_plan_destroy", "gcwt_plan_levels", "gcwt_plan_workspace_bytes",
     "gcwt_channel_means", "gcwt_execute", "gcwt_execute_host", "gcwt_filter_response",
     "gcwt_morse_kernel", "gcwt_profile_enable", "gcwt_profile_read",
-    "gcwt_fastconv", "gcwt_dft", "gcwt_analytic_signal", "gcwt_moments",
+    "gcwt_fastconv", "gcwt_dft", "gcwt_analytic_signal", "gcwt_moments", "gcwt_interp_taps",
 )
 
 
@@ -77,6 +77,7 @@ def load():
     lib.gcwt_dft.argtypes = [dp, i64, i32, dp, i32]
     lib.gcwt_analytic_signal.argtypes = [dp, i64, dp, i32]
     lib.gcwt_moments.argtypes = [vp, i32, i64, i32, dp, i32, vp]
+    lib.gcwt_interp_taps.argtypes = [i32, i32, C.c_double, C.POINTER(C.c_float)]
     lib.gcwt_profile_enable.argtypes = [vp, i32]
     lib.gcwt_profile_read.argtypes = [vp, dp, C.POINTER(i64), i32]
     _lib = lib

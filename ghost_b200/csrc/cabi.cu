@@ -322,6 +322,10 @@ int gcwt_execute_host(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_ch
     return rc;
 }
 
+int gcwt_interp_taps(int32_t log2_u, int32_t n_taps, double oversampling, float* out_host) {
+    return interp_taps(log2_u, n_taps, oversampling, out_host);
+}
+
 int gcwt_filter_response(int64_t length, int32_t k_first, int32_t n_terms, const double* terms,
                          int64_t n_fft, int64_t first_bin, int64_t n_bins, double* out_host,
                          int32_t device) {

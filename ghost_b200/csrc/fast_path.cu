@@ -23,6 +23,7 @@
 #include "multiplier.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <type_traits>
 
@@ -189,22 +190,25 @@ static void class_geometry(FastClass& fc) {
 // d_t = tap position relative to the output.  Worst-case error over ALL tones in the band (not
 // just typical spectra): 8 taps 3e-6 at os = 4 and 6e-7 at os = 5; 14 taps 2e-7 at os = 2.5 --
 // two orders of magnitude below a Kaiser-windowed sinc of the same length.
-static double sinc_pi(double x) { return x == 0.0 ? 1.0 : std::sin(M_PI * x) / (M_PI * x); }
+static long double sinc_pi(long double x) {
+    const long double pi = 3.14159265358979323846264338327950288L;
+    return x == 0.0L ? 1.0L : sinl(pi * x) / (pi * x);
+}
 
 static void design_interpolator(int log2u, std::vector<float>& coef, int T, double os) {
     const int U = 1 << log2u;
-    const double fmax = 0.5 / os;
+    const long double fmax = 0.5L / (long double)os;
     coef.resize((size_t)U * T);
     std::vector<long double> A((size_t)T * T), b(T);
-    for (int phi = 0; phi < U; ++phi) {
+    for (int t = 0; t < T; ++t) coef[t] = (t == T / 2 - 1) ? 1.f : 0.f;   // phase 0 sits on a coarse sample
+    for (int phi = 1; phi < U; ++phi) {
         for (int t = 0; t < T; ++t) {
-            const double dt = (double)(t - (T / 2 - 1)) - (double)phi / U;
-            for (int u = 0; u < T; ++u) A[(size_t)t * T + u] = sinc_pi(2.0 * fmax * (double)(t - u));
-            A[(size_t)t * T + t] += 1e-14L;
-            b[t] = sinc_pi(2.0 * fmax * dt);
+            const long double dt = (long double)(t - (T / 2 - 1)) - (long double)phi / U;
+            for (int u = 0; u < T; ++u) A[(size_t)t * T + u] = sinc_pi(2.0L * fmax * (long double)(t - u));
+            b[t] = sinc_pi(2.0L * fmax * dt);
         }
-        // Gaussian elimination with partial pivoting (the system is small and ill-conditioned:
-        // extended precision keeps the solution good to ~1e-8)
+        // Gaussian elimination with partial pivoting in extended precision: the system is small and
+        // ill-conditioned (1e13 for 8 taps), and a ridge term would buy stability with out-of-band gain
         for (int i = 0; i < T; ++i) {
             int piv = i;
             for (int r = i + 1; r < T; ++r) if (fabsl(A[(size_t)r * T + i]) > fabsl(A[(size_t)piv * T + i])) piv = r;
@@ -227,6 +231,17 @@ static void design_interpolator(int log2u, std::vector<float>& coef, int T, doub
         for (int t = 0; t < T; ++t) sum += c[t];
         for (int t = 0; t < T; ++t) coef[(size_t)phi * T + t] = (float)(c[t] / sum);   // exact DC gain
     }
+}
+
+int interp_taps(int log2u, int n_taps, double os, float* out) {
+    if (log2u < 0 || log2u > 20 || n_taps < 4 || n_taps > 32 || (n_taps & 1) || !(os >= 1.0) || !out) {
+        set_error("interp_taps: log2_u in 0..20, n_taps even in 4..32, oversampling >= 1 required");
+        return GCWT_ERR_ARG;
+    }
+    std::vector<float> coef;
+    design_interpolator(log2u, coef, n_taps, os);
+    std::copy(coef.begin(), coef.end(), out);
+    return GCWT_OK;
 }
 
 static int upload_constants(const gcwt_plan* p) {
@@ -1122,8 +1137,25 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
     GCWT_CUDA_OK(cudaGetLastError());
 
     // ---- fused kernels ---------------------------------------------------------------
+    // The classes are independent (disjoint output rows, read-only inputs).  With GCWT_STREAMS = k > 1
+    // they are dealt round-robin to k streams that fork from and join `st`, so that the tail of one
+    // launch overlaps the head of the next and compute-bound and HBM-bound classes share the SMs.
+    static cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    int n_side = 0, ci = 0;
+    if (const char* e = getenv("GCWT_STREAMS")) n_side = std::max(0, std::min(3, atoi(e) - 1));
+    if (n_side > 0) {
+        if (!ev_fork) cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+        cudaEventRecord(ev_fork, st);
+        for (int k = 0; k < n_side; ++k) {
+            if (!side[k]) { cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming); }
+            cudaStreamWaitEvent(side[k], ev_fork, 0);
+        }
+    }
     for (const FastClass& fc : p->classes) {
-        const int sp = prof_begin(p, fc.level < 0 ? 1 : (fc.interp ? 4 : 2), st, fc.level + 2);
+        cudaStream_t cs = st;
+        if (n_side > 0) { cs = (ci % (n_side + 1)) ? side[(ci % (n_side + 1)) - 1] : st; ++ci; }
+        const int sp = prof_begin(p, fc.level < 0 ? 1 : (fc.interp ? 4 : 2), cs, fc.level + 2);
         // (an interpolated class that falls back to the direct kernel is still booked as [4])
         FusedParams prm;
         prm.means = d_means;
@@ -1158,13 +1190,13 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
             if (fc.wide) {
                 if (p->out_kind == GCWT_OUT_AMPLITUDE)
-                    fused_interp_kernel<GCWT_OUT_AMPLITUDE, true><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
+                    fused_interp_kernel<GCWT_OUT_AMPLITUDE, true><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
                 else
-                    fused_interp_kernel<GCWT_OUT_POWER, true><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
+                    fused_interp_kernel<GCWT_OUT_POWER, true><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
             } else if (p->out_kind == GCWT_OUT_AMPLITUDE)
-                fused_interp_kernel<GCWT_OUT_AMPLITUDE, false><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
+                fused_interp_kernel<GCWT_OUT_AMPLITUDE, false><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
             else
-                fused_interp_kernel<GCWT_OUT_POWER, false><<<(unsigned)nblk, 256, kInterpSmem, st>>>(prm);
+                fused_interp_kernel<GCWT_OUT_POWER, false><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
         } else if (fc.level >= 0) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1176,17 +1208,18 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.units_per_chunk = (blocks + prm.iters - 1) / prm.iters;
             const int64_t nblk = n_channels * prm.n_chunks * prm.units_per_chunk;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
-            launch_banded(p->out_kind, prm.log2p, (unsigned)nblk, st, prm);
+            launch_banded(p->out_kind, prm.log2p, (unsigned)nblk, cs, prm);
         } else {
             prm.src = x; prm.src_stride = x_stride; prm.src_lo = -halo_l; prm.src_hi = n + halo_r;
             prm.log2d = 0; prm.p_cols = 16; prm.log2p = 4; prm.iters = 1; prm.units_per_chunk = 1;
             const int64_t nblk = n_channels * prm.n_chunks;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
-            launch_full<TIn>(p->out_kind, (unsigned)nblk, st, prm);
+            launch_full<TIn>(p->out_kind, (unsigned)nblk, cs, prm);
         }
         count_launch();
-        prof_end(p, sp, st);
+        prof_end(p, sp, cs);
     }
+    for (int k = 0; k < n_side; ++k) { cudaEventRecord(ev_join[k], side[k]); cudaStreamWaitEvent(st, ev_join[k], 0); }
     GCWT_CUDA_OK(cudaGetLastError());
     return GCWT_OK;
 }

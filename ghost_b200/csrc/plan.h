@@ -117,6 +117,7 @@ int fast_execute(gcwt_plan* p, const void* x, int in_type,
                  int64_t n_channels, int64_t n_samples, int64_t x_stride,
                  int64_t halo_l, int64_t halo_r, const double* d_means,
                  void* out, int64_t s_stride, int64_t c_stride, cudaStream_t st);
+int interp_taps(int log2u, int n_taps, double os, float* out);   // host: the interpolator design
 int fast_plan_build(gcwt_plan* p);       // classify scales + upload tables (fp32 plans)
 void fast_plan_free(gcwt_plan* p);
 int means_blocks(int64_t n_samples);

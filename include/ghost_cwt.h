@@ -131,6 +131,13 @@ int gcwt_filter_response(int64_t length, int32_t k_first, int32_t n_terms,
 int gcwt_morse_kernel(int64_t length, int32_t k_first, int32_t n_terms, const double *terms,
                       double *out_host, int32_t device);
 
+/* Taps of the polyphase interpolator that brings |W|^2 from the coarse grid (spacing U = 2^log2_u
+ * samples) to the full rate on the amplitude / power paths: least-squares fractional-delay fit over
+ * the band |f| <= 1 / (2 * oversampling) cycles per coarse sample.  Host-only (no device needed).
+ * Writes U * n_taps floats, phase-major: output at coarse position iota + phi / U is
+ * sum_t taps[phi][t] * p[iota + t - (n_taps / 2 - 1)].  n_taps even, 4 .. 32. */
+int gcwt_interp_taps(int32_t log2_u, int32_t n_taps, double oversampling, float *out_host);
+
 /* ---- sigtools helpers; host pointers, complex128 like the reference ----
  *
  * gcwt_fastconv: full linear convolution, n + m - 1 complex outputs (interleaved re, im).  Replaces
