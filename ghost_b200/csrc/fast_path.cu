@@ -526,6 +526,27 @@ __device__ __forceinline__ unsigned valid_mask(int rel, int sh, int lo, int hi) 
     return k_hi > k_lo ? (((1u << k_hi) - 1u) & ~((1u << k_lo) - 1u)) : 0u;
 }
 
+// Mean of the chunk a block is about to transform (NV values per thread, 256 threads).  Every filter
+// has exactly zero response at bin 0 (the reference forces X[0] = 0, morseutils.py:178), so ANY constant
+// may be subtracted from the whole chunk -- zero padding included -- without changing a kept output.
+// Subtracting the chunk's own mean keeps the fp32 butterflies from rounding at the scale of a slow
+// drift: with red (1/f^2) recordings the error of the high-frequency scales drops several-fold.
+// `scratch` is 8 floats of shared memory that nobody else touches until the next barrier.
+template <int NV>
+__device__ __forceinline__ float chunk_mean(const float* v, float* scratch) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s += v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = s;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += scratch[w];
+    return t * (1.0f / (float)(NV * 256));
+}
+
 // 1024-point forward FFT: five radix-4 Stockham passes, 256 threads, one butterfly per thread and
 // pass.  Thread j handles butterfly j in every pass, so all of its 12 twiddles are fetched up
 // front in one batch of independent loads (one memory latency instead of four in a chain).
@@ -633,8 +654,9 @@ fused_banded_kernel(const FusedParams prm) {
             const int64_t u = i0 + tid + 256 * k;
             raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
         }
+        const float cm = chunk_mean<kChunkDec / 256>(raw, (float*)Zs);
 #pragma unroll
-        for (int k = 0; k < kChunkDec / 256; ++k) ex[tid + 256 * k] = make_float2(raw[k], 0.f);
+        for (int k = 0; k < kChunkDec / 256; ++k) ex[tid + 256 * k] = make_float2(raw[k] - cm, 0.f);
         __syncthreads();
         float2* Y = smem_fft1024_forward(ex, ex + kChunkDec, prm.twf);
         // ---- (2) multiply by every scale's response (bins 0..255) ---------------
@@ -873,8 +895,9 @@ fused_interp_kernel(const FusedParams prm) {
             const int64_t u = i0 + tid + 256 * k;
             raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
         }
+        const float cm = chunk_mean<kChunkDec / 256>(raw, (float*)Zs);
 #pragma unroll
-        for (int k = 0; k < kChunkDec / 256; ++k) ex[tid + 256 * k] = make_float2(raw[k], 0.f);
+        for (int k = 0; k < kChunkDec / 256; ++k) ex[tid + 256 * k] = make_float2(raw[k] - cm, 0.f);
         __syncthreads();
         float2* Y = smem_fft1024_forward(ex, ex + kChunkDec, prm.twf);
         const float2 y = Y[tid];
@@ -1001,9 +1024,13 @@ fused_full_kernel(const FusedParams prm) {
             raw[k] = ok ? src[u] : (TIn)0;
             inside |= (unsigned)ok << k;
         }
+        float val[kFullN / 256];
 #pragma unroll
         for (int k = 0; k < kFullN / 256; ++k)                    // zero padding outside the readable range
-            A[tid + 256 * k] = make_float2((inside >> k & 1) ? (float)((double)raw[k] - mu) : 0.f, 0.f);
+            val[k] = (inside >> k & 1) ? (float)((double)raw[k] - mu) : 0.f;
+        const float cm = chunk_mean<kFullN / 256>(val, (float*)ex + 2048);   // (behind the forward FFT's spill into ex)
+#pragma unroll
+        for (int k = 0; k < kFullN / 256; ++k) A[tid + 256 * k] = make_float2(val[k] - cm, 0.f);
         __syncthreads();
         smem_fft4096_forward(A, Yf, prm.twf);
     }
