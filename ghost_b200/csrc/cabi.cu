@@ -181,6 +181,11 @@ int gcwt_plan_destroy(gcwt_plan* p) {
     if (p->d_means) cudaFree(p->d_means);
     if (p->d_partial) cudaFree(p->d_partial);
     if (p->d_twiddle) cudaFree(p->d_twiddle);
+    for (int k = 0; k < gcwt_plan::kSideStreams; ++k) {
+        if (p->side_stream[k]) { cudaStreamSynchronize(p->side_stream[k]); cudaStreamDestroy(p->side_stream[k]); }
+        if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]);
+    }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     delete p;
     return GCWT_OK;
 }

@@ -1164,25 +1164,14 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
     GCWT_CUDA_OK(cudaGetLastError());
 
     // ---- fused kernels ---------------------------------------------------------------
-    // The classes are independent (disjoint output rows, read-only inputs).  With GCWT_STREAMS = k > 1
-    // they are dealt round-robin to k streams that fork from and join `st`, so that the tail of one
-    // launch overlaps the head of the next and compute-bound and HBM-bound classes share the SMs.
-    static cudaStream_t side[3] = {nullptr, nullptr, nullptr};
-    static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
-    int n_side = 0, ci = 0;
-    if (const char* e = getenv("GCWT_STREAMS")) n_side = std::max(0, std::min(3, atoi(e) - 1));
-    if (n_side > 0) {
-        if (!ev_fork) cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-        cudaEventRecord(ev_fork, st);
-        for (int k = 0; k < n_side; ++k) {
-            if (!side[k]) { cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming); }
-            cudaStreamWaitEvent(side[k], ev_fork, 0);
-        }
-    }
-    for (const FastClass& fc : p->classes) {
-        cudaStream_t cs = st;
-        if (n_side > 0) { cs = (ci % (n_side + 1)) ? side[(ci % (n_side + 1)) - 1] : st; ++ci; }
-        const int sp = prof_begin(p, fc.level < 0 ? 1 : (fc.interp ? 4 : 2), cs, fc.level + 2);
+    // the thread <-> interval interpolators (U = 2, 4 and the wide classes) write 128-bit vectors:
+    // rows must be 16-byte aligned, else the class falls back to the direct kernel
+    const bool rows_aligned = ((uintptr_t)out % 16 == 0) && (s_stride % 4 == 0) && (c_stride % 4 == 0);
+    auto uses_interp = [&](const FastClass& fc) {
+        return fc.level >= 0 && fc.interp && ((fc.log2u >= 3 && !fc.wide) || rows_aligned);
+    };
+    auto launch_class = [&](const FastClass& fc, cudaStream_t cs, bool own_span) -> int {
+        const int sp = own_span ? prof_begin(p, fc.level < 0 ? 1 : (fc.interp ? 4 : 2), cs, fc.level + 2) : -1;
         // (an interpolated class that falls back to the direct kernel is still booked as [4])
         FusedParams prm;
         prm.means = d_means;
@@ -1194,10 +1183,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prm.out = out; prm.s_stride = s_stride; prm.c_stride = c_stride;
         prm.inv_nc = 1.0f / (float)fc.nc_full;
         prm.log2u = fc.log2u; prm.coef = fc.d_coef; prm.twf = p->d_twiddle; prm.scale_nmu = fc.d_scale_nmu;
-        // the thread <-> interval interpolators (U = 2, 4 and the wide classes) write 128-bit vectors:
-        // rows must be 16-byte aligned
-        const bool rows_aligned = ((uintptr_t)out % 16 == 0) && (s_stride % 4 == 0) && (c_stride % 4 == 0);
-        if (fc.level >= 0 && fc.interp && ((fc.log2u >= 3 && !fc.wide) || rows_aligned)) {
+        if (uses_interp(fc)) {
             // (an unaligned wide class falls through to the direct kernel with its own geometry)
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1245,8 +1231,51 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         }
         count_launch();
         prof_end(p, sp, cs);
+        return GCWT_OK;
+    };
+
+    // full-spectrum and direct classes: one after the other on the caller's stream
+    int n_group = 0;
+    for (const FastClass& fc : p->classes) {
+        if (uses_interp(fc)) { ++n_group; continue; }
+        rc = launch_class(fc, st, true);
+        if (rc) return rc;
     }
-    for (int k = 0; k < n_side; ++k) { cudaEventRecord(ev_join[k], side[k]); cudaStreamWaitEvent(st, ev_join[k], 0); }
+    // interpolated classes: independent launches (disjoint output rows, read-only inputs) of 5-20 waves
+    // each.  They are dealt to two streams that fork from and join `st`, so that the tail of one launch
+    // overlaps the head of the next (+1 % on config 2, +2.4 % on config 3 with its 8 tiles); the
+    // profiling span covers the whole group.  GCWT_STREAMS=1 (or per-class timing) serialises them.
+    if (n_group > 0) {
+        int n_streams = 2;
+        if (const char* e = getenv("GCWT_STREAMS")) n_streams = std::max(1, std::min(1 + gcwt_plan::kSideStreams, atoi(e)));
+        const bool per_class = p->profile && getenv("GCWT_CLASS_TIMES") != nullptr;
+        if (per_class || n_group < 2) n_streams = 1;
+        const int n_side = n_streams - 1;
+        for (int k = 0; k < n_side; ++k) {
+            if (!p->side_stream[k]) {
+                GCWT_CUDA_OK(cudaStreamCreateWithFlags(&p->side_stream[k], cudaStreamNonBlocking));
+                GCWT_CUDA_OK(cudaEventCreateWithFlags(&p->ev_join[k], cudaEventDisableTiming));
+            }
+        }
+        if (n_side > 0 && !p->ev_fork) GCWT_CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+        const int sp = per_class ? -1 : prof_begin(p, 4, st, 63);
+        if (n_side > 0) {
+            GCWT_CUDA_OK(cudaEventRecord(p->ev_fork, st));
+            for (int k = 0; k < n_side; ++k) GCWT_CUDA_OK(cudaStreamWaitEvent(p->side_stream[k], p->ev_fork, 0));
+        }
+        int ci = 0;
+        for (const FastClass& fc : p->classes) {
+            if (!uses_interp(fc)) continue;
+            const int slot = ci++ % n_streams;
+            rc = launch_class(fc, slot ? p->side_stream[slot - 1] : st, per_class);
+            if (rc) return rc;
+        }
+        for (int k = 0; k < n_side; ++k) {
+            GCWT_CUDA_OK(cudaEventRecord(p->ev_join[k], p->side_stream[k]));
+            GCWT_CUDA_OK(cudaStreamWaitEvent(st, p->ev_join[k], 0));
+        }
+        prof_end(p, sp, st);
+    }
     GCWT_CUDA_OK(cudaGetLastError());
     return GCWT_OK;
 }

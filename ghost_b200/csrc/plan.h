@@ -96,6 +96,9 @@ struct gcwt_plan {
     float2* d_twiddle = nullptr;            // e^{-2 pi i k / 4096}, k < 4096 (forward FFTs of the fused kernels)
     double* d_means = nullptr;              // internal per-channel means
     int64_t means_cap = 0;
+    static constexpr int kSideStreams = 3;
+    cudaStream_t side_stream[kSideStreams] = {nullptr, nullptr, nullptr};   // forked streams of the interpolated classes
+    cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {nullptr, nullptr, nullptr};
     double* d_partial = nullptr;            // scratch of the mean reduction
     int64_t partial_cap = 0;
 };

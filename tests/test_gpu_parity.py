@@ -415,3 +415,37 @@ def test_cfg2_shape_properties():
     rhs = 2 * pc.execute(xs, means=zero)[0] + pc.execute(y, means=zero)[0]
     rel = (torch.linalg.vector_norm(lhs - rhs, dim=1) / torch.linalg.vector_norm(rhs, dim=1)).max().item()
     assert rel <= 5e-6
+
+
+def test_fp32_red_noise_recording():
+    """A random walk plus an offset (1/f^2 spectrum, like a drifting LFP baseline): the drift inside a
+    chunk is what fp32 FFT butterflies round against, so every fused kernel subtracts the chunk's own
+    mean first (exact: all filters have zero DC response).  Odd length: rows are not 16-byte aligned."""
+    fs, n = 1250.0, 150001
+    rng = np.random.default_rng(7)
+    x = (np.cumsum(rng.standard_normal(n)) * 0.05 + rng.standard_normal(n) + 2.5).astype(np.float32)
+    amp, f, _ = orc.cwt_amplitude(x.astype(np.float64), fs, freq_limits=[1.0, 400.0], parallel=True)
+    for nn in (n, n - 1):                                       # unaligned and aligned output rows
+        cwt = ContinuousWaveletTransform(dtype=np.float32)
+        cwt.transform(x[:nn], fs=fs, freq_limits=[1.0, 400.0])
+        if nn != n:
+            amp, f, _ = orc.cwt_amplitude(x[:nn].astype(np.float64), fs, freq_limits=[1.0, 400.0], parallel=True)
+        lev = cwt.last_plan.levels()
+        assert lev.min() == -1 and lev.max() >= 5
+        err = _l2rel(cwt.amplitude.astype(np.float64), amp)
+        assert err.max() <= FP32_BAR, (nn, int(np.argmax(err)), err.max(), lev.tolist())
+        assert err.max() <= 5e-6, (nn, err.max())              # what the chunk-mean removal leaves
+
+
+def test_multi_stream_class_launches_are_bit_identical(monkeypatch):
+    """GCWT_STREAMS = k deals the independent scale-class launches to k forked streams: same kernels,
+    same data, bit-identical results."""
+    fs, n, nch = 1250.0, 60000, 3
+    X = synth.recording(nch, n, fs, np.float32)
+    outs = []
+    for k in ("1", "3"):
+        monkeypatch.setenv("GCWT_STREAMS", k)
+        cwt = ContinuousWaveletTransform(dtype=np.float32, output="power")
+        cwt.transform(X, fs=fs, multichannel=True, freq_limits=[1, 400])
+        outs.append(cwt.power.copy())
+    assert np.array_equal(outs[0], outs[1])
