@@ -80,7 +80,8 @@ static double halfband_gain(const double* odd, double theta) {
 // Per scale: kBins values on each candidate grid 1024 << level (level = kMinFastLevel ...
 // kMaxFastLevel) followed by kFullN values on the 4096-point grid.
 constexpr int kPlanLevels = kMaxFastLevel - kMinFastLevel + 1;
-constexpr int kPlanRow = kPlanLevels * kBins + kFullN;
+constexpr int kWide2Levels = kWideMaxLevel - kMinFastLevel + 1;      // levels that may run fused_wide2_kernel
+constexpr int kPlanRow = kPlanLevels * kBins + kFullN + kWide2Levels * 2 * kBins;
 
 __global__ void plan_response_kernel(const ScaleInfo* __restrict__ scales, const double* __restrict__ terms,
                                      double* __restrict__ out) {
@@ -90,7 +91,11 @@ __global__ void plan_response_kernel(const ScaleInfo* __restrict__ scales, const
     const ScaleInfo sc = scales[s];
     int64_t n, m;
     if (i < kPlanLevels * kBins) { n = (int64_t)kChunkDec << (kMinFastLevel + i / kBins); m = i % kBins; }
-    else { n = kFullN; m = i - kPlanLevels * kBins; }
+    else if (i < kPlanLevels * kBins + kFullN) { n = kFullN; m = i - kPlanLevels * kBins; }
+    else {
+        const int k = i - kPlanLevels * kBins - kFullN;
+        n = (int64_t)(2 * kChunkDec) << (kMinFastLevel + k / (2 * kBins)); m = k % (2 * kBins);
+    }
     out[(int64_t)s * kPlanRow + i] = morse_response(m, n, sc.L, sc.k_first, sc.n_terms, terms + sc.term_off);
 }
 
@@ -98,6 +103,9 @@ struct PlanResponses {
     std::vector<double> g;                      // [n_scales][kPlanRow]
     const double* level(int s, int lev) const { return g.data() + (size_t)s * kPlanRow + (size_t)(lev - kMinFastLevel) * kBins; }
     const double* full(int s) const { return g.data() + (size_t)s * kPlanRow + (size_t)kPlanLevels * kBins; }
+    const double* wide2(int s, int lev) const {
+        return g.data() + (size_t)s * kPlanRow + (size_t)kPlanLevels * kBins + kFullN + (size_t)(lev - kMinFastLevel) * 2 * kBins;
+    }
 };
 
 static int compute_plan_responses(const gcwt_plan* p, PlanResponses& pr) {
@@ -317,6 +325,35 @@ int fast_plan_build(gcwt_plan* p) {
             }
             class_geometry(fc);
             if (fc.hop <= 0) { set_error("planner: non-positive hop"); return GCWT_ERR_ARG; }
+#ifndef GCWT_NO_WIDE2
+            if (fc.wide) {                                        // same margins on the 2x longer chunk
+                const int64_t d = int64_t(1) << level, align = std::max<int64_t>(d, 16), nc2 = 2 * fc.nc_full;
+                const int64_t lead = (int64_t)(kWideT / 2 - 1) << fc.log2u, tail = (int64_t)(kWideT / 2 + 1) << fc.log2u;
+                fc.offset2 = ((fc.lmax / 2 + lead + align - 1) / align) * align;
+                fc.hop2 = ((nc2 - (fc.lmax - 1) / 2 - tail - fc.offset2) / align) * align;
+                const int ns2 = (int)fc.scale_ids.size();
+                std::vector<float2> tab2((size_t)ns2 * 2 * kBins);
+                for (int i = 0; i < ns2; ++i) {
+                    const ScaleInfo& sc = p->scales[fc.scale_ids[i]];
+                    const double* gsrc = pr.wide2(fc.scale_ids[i], level);
+                    for (int m = 0; m < 2 * kBins; ++m) {
+                        double g = gsrc[m] / (double)(2 * kChunkDec);
+                        // decimator: stage i of `level` runs at theta = 2 pi m 2^(i-1) / (2048 D)
+                        for (int j = 1; j <= level; ++j)
+                            g /= halfband_gain(p->halfband_odd, 2.0 * M_PI * (double)m / (double)((int64_t)(2 * kChunkDec) << j));
+                        double re = g, im = 0.0;
+                        if ((sc.L & 1) == 0) {
+                            const double ph = -M_PI * (double)m / (double)nc2;
+                            re = g * std::cos(ph);
+                            im = g * std::sin(ph);
+                        }
+                        tab2[(size_t)i * 2 * kBins + m] = make_float2((float)re, (float)im);
+                    }
+                }
+                GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_table2, sizeof(float2) * tab2.size()));
+                GCWT_CUDA_OK(cudaMemcpy(fc.d_table2, tab2.data(), sizeof(float2) * tab2.size(), cudaMemcpyHostToDevice));
+            }
+#endif
             const int nb = level >= 0 ? kBins : kFullN;
             const int ns = (int)fc.scale_ids.size();
             std::vector<float2> tab((size_t)ns * nb);
@@ -370,6 +407,7 @@ int fast_plan_build(gcwt_plan* p) {
 void fast_plan_free(gcwt_plan* p) {
     for (auto& fc : p->classes) {
         if (fc.d_table) cudaFree(fc.d_table);
+        if (fc.d_table2) cudaFree(fc.d_table2);
         if (fc.d_scale_ids) cudaFree(fc.d_scale_ids);
         if (fc.d_coef) cudaFree(fc.d_coef);
         if (fc.d_scale_nmu) cudaFree(fc.d_scale_nmu);
@@ -975,6 +1013,146 @@ fused_interp_kernel(const FusedParams prm) {
     }
 }
 
+// ---------------------------------------------------------------------------- wide classes, long chunks
+// The wide classes (levels 2-3, U = D) pay most for their coarse transforms, so they use chunks of
+// 2048 decimated samples with 512 bins kept: overlap-save efficiency 0.90 instead of 0.80 and half
+// the per-chunk fixed cost.  The 512 useful bins of the chunk's spectrum stay in registers (two per
+// thread); W on the coarse grid is a 2048-point inverse transform with 512 non-zero bins = 8 columns
+// of 256-point transforms, two scales per 16-lane pass: the two alias blocks of a bin are folded
+// onto the 8 columns in registers (an 8-point DFT with two inputs), then the usual 16 x 16 passes.
+// |W|^2 lands in shared memory (aliasing the exchange tile) and the thread <-> interval interpolator
+// of the wide classes brings it to the full rate.
+// smem: B0[4096] (FFT ping, then exchange) | B1[4096] (FFT pong, then alias tile / coarse rows) | ids
+constexpr size_t kWide2Smem = sizeof(float2) * 2 * 4096 + sizeof(int) * kMaxClassScales;
+
+// Bins 0 .. 511 of the 2048-point forward FFT of the real chunk in `a` (2048 float2, imaginary parts
+// zero): five radix-4 Stockham passes (two butterflies per thread), then the last radix-2 pass only
+// for the bins that are kept, straight into registers (y0 = bin tid, y1 = bin tid + 256).
+__device__ __forceinline__ void smem_fft2048_forward_low(float2* a, float2* b, const float2* __restrict__ tw,
+                                                         float2& y0, float2& y1) {
+    constexpr int N = 2 * kChunkDec, M = N / 4;                     // 512 butterflies per pass
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+        const int ns = 1 << (2 * p);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = tid + 256 * h;
+            const int k = j & (ns - 1);
+            float2 v0 = a[j], v1 = a[j + M], v2 = a[j + 2 * M], v3 = a[j + 3 * M];
+            if (p > 0) {
+                const int idx = k * ((kFullN / 4) / ns);            // e^{-2 pi i t k / (4 ns)} = tw[t k 4096 / (4 ns)]
+                v1 = cmul(v1, __ldg(tw + idx));
+                v2 = cmul(v2, __ldg(tw + 2 * idx));
+                v3 = cmul(v3, __ldg(tw + 3 * idx));
+            }
+            dft4<-1>(v0, v1, v2, v3);
+            const int j0 = ((j - k) << 2) + k;
+            b[j0] = v0; b[j0 + ns] = v1; b[j0 + 2 * ns] = v2; b[j0 + 3 * ns] = v3;
+        }
+        __syncthreads();
+        float2* t = a; a = b; b = t;
+    }
+    // radix-2: bin j = a[j] + e^{-2 pi i j / 2048} a[j + 1024], j < 1024; only j < 512 is needed
+    y0 = cadd(a[tid], cmul(a[tid + N / 2], __ldg(tw + 2 * tid)));
+    y1 = cadd(a[tid + 256], cmul(a[tid + 256 + N / 2], __ldg(tw + 2 * (tid + 256))));
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 2)
+fused_wide2_kernel(const FusedParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* B0 = (float2*)smem_raw;
+    float2* B1 = B0 + 4096;
+    int* s_ids = (int*)(B1 + 4096);
+
+    const int tid = threadIdx.x;
+    const int r = tid & 15;
+    const int g = tid >> 4;
+    const int64_t q = blockIdx.x % prm.n_chunks;
+    const int64_t c = blockIdx.x / prm.n_chunks;
+    const int64_t t0 = q * prm.hop - prm.offset;
+    const int lu = prm.log2u;
+    const int own_lo = (int)prm.offset;
+    const int own_hi = (int)min(prm.offset + prm.hop, prm.n - t0);
+    const int ia = own_lo >> lu, ib = (own_hi + (1 << lu) - 1) >> lu;
+    if (tid < prm.n_scales) s_ids[tid] = prm.scale_ids[tid];
+
+    float2 y0, y1;                                                 // spectrum bins tid and tid + 256
+    {
+        constexpr int NV = 2 * kChunkDec / 256;
+        const float* src = (const float*)prm.src + c * prm.src_stride - prm.src_lo;
+        const int64_t i0 = t0 >> prm.log2d;                        // exact: t0 is a multiple of D
+        float raw[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int64_t u = i0 + tid + 256 * k;
+            raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
+        }
+        const float cm = chunk_mean<NV>(raw, (float*)(B1 + 3072));
+#pragma unroll
+        for (int k = 0; k < NV; ++k) B0[tid + 256 * k] = make_float2(raw[k] - cm, 0.f);
+        __syncthreads();
+        smem_fft2048_forward_low(B0, B1, prm.twf, y0, y1);
+    }
+    float2 tw[16], tw2k[8];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tw[k] = tw_pos(prm.twf, 16 * g * k);          // e^{2 pi i g k / 256}
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tw2k[k] = tw_pos(prm.twf, 2 * tid * k);        // e^{2 pi i m' k / 2048}
+    float* const out_c = (float*)prm.out + c * prm.c_stride + t0;
+    float2* const A = B1;
+    float2* const ex = B0;
+    float* const Pc = (float*)B1;
+    const int col = r & 7, sidx = r >> 3;
+    __syncthreads();                                               // the spectrum is in registers: both buffers are free
+    for (int pair = 0; pair < prm.n_scales; pair += 2) {
+        // the two alias blocks (bins m' and m' + 256) folded onto the 8 columns, both scales of the pass
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            const int s = min(pair + sl, prm.n_scales - 1);
+            const float2* tab = prm.table + (int64_t)s * (2 * kBins) + tid;
+            const float2 z0 = cmul(y0, __ldg(tab));
+            const float2 z1 = cmul(y1, __ldg(tab + kBins));
+            const float h = 0.70710678118654752440f;
+            const float2 zr = make_float2((z1.x - z1.y) * h, (z1.x + z1.y) * h);   // z1 e^{i pi/4}
+            float2 v[8];
+            v[0] = cadd(z0, z1);            v[4] = csub(z0, z1);
+            v[2] = cadd(z0, mul_i<+1>(z1)); v[6] = csub(z0, mul_i<+1>(z1));
+            v[1] = cadd(z0, zr);            v[5] = csub(z0, zr);
+            v[3] = cadd(z0, mul_i<+1>(zr)); v[7] = csub(z0, mul_i<+1>(zr));
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                A[tid * 16 + ((sl * 8 + k) ^ (tid & 15))] = k ? cmul(v[k], tw2k[k]) : v[k];
+        }
+        __syncthreads();
+        float2 a[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 16 + (r ^ g)];
+        dft16<+1>(a);
+        float2* e = ex + (g * 16) * 16 + r;
+        e[0] = a[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
+        __syncthreads();                                           // all reads of A are done: the coarse rows may overwrite it
+        const float2* e2 = ex + g * 16 + r;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
+        dft16<+1>(a);
+        float* pc = Pc + sidx * kPcStride + g * 8 + col;           // coarse index (g + 16 k) * 8 + col
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pc[k * 128] = a[k].x * a[k].x + a[k].y * a[k].y;
+        __syncthreads();
+        for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl) {
+            const float* pcs = Pc + sl * kPcStride;
+            float* row = out_c + (int64_t)s_ids[pair + sl] * prm.s_stride;
+            if (lu == 2) interp_rows_wide<KIND, 2>(pcs, row, ia, ib, own_hi);
+            else interp_rows_wide<KIND, 3>(pcs, row, ia, ib, own_hi);
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------- full spectrum
 // smem: Yf[4096] | ex[4096] | A[4096] | ids[64] | nmu[64]
 constexpr size_t kFullSmem = sizeof(float2) * 3 * 4096 + sizeof(int) * 2 * kMaxFullScales;
@@ -1183,7 +1361,21 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prm.out = out; prm.s_stride = s_stride; prm.c_stride = c_stride;
         prm.inv_nc = 1.0f / (float)fc.nc_full;
         prm.log2u = fc.log2u; prm.coef = fc.d_coef; prm.twf = p->d_twiddle; prm.scale_nmu = fc.d_scale_nmu;
-        if (uses_interp(fc)) {
+        if (uses_interp(fc) && fc.wide && fc.d_table2) {
+            const LevelGeom& g = lv[fc.level];
+            prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
+            prm.log2d = fc.level;
+            prm.offset = fc.offset2; prm.hop = fc.hop2;
+            prm.n_chunks = (n + fc.hop2 - 1) / fc.hop2;
+            prm.table = fc.d_table2;
+            prm.p_cols = 8; prm.log2p = 3; prm.iters = 1; prm.units_per_chunk = 1;
+            const int64_t nblk = n_channels * prm.n_chunks;
+            if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
+            if (p->out_kind == GCWT_OUT_AMPLITUDE)
+                fused_wide2_kernel<GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kWide2Smem, cs>>>(prm);
+            else
+                fused_wide2_kernel<GCWT_OUT_POWER><<<(unsigned)nblk, 256, kWide2Smem, cs>>>(prm);
+        } else if (uses_interp(fc)) {
             // (an unaligned wide class falls through to the direct kernel with its own geometry)
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1288,6 +1480,8 @@ static int set_smem_attrs() {
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_wide2_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWide2Smem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_wide2_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWide2Smem));
     return GCWT_OK;
 }
 

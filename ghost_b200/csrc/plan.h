@@ -60,6 +60,10 @@ struct FastClass {
     int32_t* d_scale_nmu = nullptr;
     bool interp = false;
     bool wide = false;              // coarse spacing U = D (4 columns), kWideT taps; else U = D/2, kInterpT taps
+    // wide classes with 16-byte aligned rows run on chunks of 2 * kChunkDec decimated samples with
+    // 2 * kBins bins kept (fused_wide2_kernel): own table [n][2 kBins] and overlap-save geometry
+    float2* d_table2 = nullptr;
+    int64_t offset2 = 0, hop2 = 0;
     int log2u = 0;
     float* d_coef = nullptr;
 };
