@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=None, help="override samples per channel")
     ap.add_argument("--channels", type=int, default=None, help="channels per GPU (default: workload's)")
+    ap.add_argument("--tile", type=int, default=None, help="samples per time tile (tiled workloads)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
@@ -220,7 +221,7 @@ def run_ours(args):
         if c >= len(base):
             x_host[c] = torch.roll(x_host[c], 1009 * c)
     x_dev = x_host.to(dev, non_blocking=True)
-    tile = int(wl.get("tile", 0))
+    tile = int(args.tile if args.tile else wl.get("tile", 0))
     out = plan.alloc_out(nch, tile if tile else n)
     step_means = plan.channel_means(x_dev) if tile else None
     torch.cuda.synchronize(dev)
