@@ -1022,8 +1022,9 @@ fused_interp_kernel(const FusedParams prm) {
 // onto the 8 columns in registers (an 8-point DFT with two inputs), then the usual 16 x 16 passes.
 // |W|^2 lands in shared memory (aliasing the exchange tile) and the thread <-> interval interpolator
 // of the wide classes brings it to the full rate.
-// smem: B0[4096] (FFT ping, then exchange) | B1[4096] (FFT pong, then alias tile / coarse rows) | ids
-constexpr size_t kWide2Smem = sizeof(float2) * 2 * 4096 + sizeof(int) * kMaxClassScales;
+// smem: B0[4096] (FFT ping, then exchange) | B1[256 x 17] (FFT pong, then alias tile / coarse rows) | ids
+constexpr int kTileA = 256 * 17;   // alias tile: 16 columns per bin, rows padded to 17 (conflict-free, constant offsets)
+constexpr size_t kWide2Smem = sizeof(float2) * (4096 + kTileA) + sizeof(int) * kMaxClassScales;
 
 // Bins 0 .. 511 of the 2048-point forward FFT of the real chunk in `a` (2048 float2, imaginary parts
 // zero): five radix-4 Stockham passes (two butterflies per thread), then the last radix-2 pass only
@@ -1064,7 +1065,7 @@ fused_wide2_kernel(const FusedParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* B0 = (float2*)smem_raw;
     float2* B1 = B0 + 4096;
-    int* s_ids = (int*)(B1 + 4096);
+    int* s_ids = (int*)(B1 + kTileA);
 
     const int tid = threadIdx.x;
     const int r = tid & 15;
@@ -1123,12 +1124,12 @@ fused_wide2_kernel(const FusedParams prm) {
             v[3] = cadd(z0, mul_i<+1>(zr)); v[7] = csub(z0, mul_i<+1>(zr));
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                A[tid * 16 + ((sl * 8 + k) ^ (tid & 15))] = k ? cmul(v[k], tw2k[k]) : v[k];
+                A[tid * 17 + sl * 8 + k] = k ? cmul(v[k], tw2k[k]) : v[k];
         }
         __syncthreads();
         float2 a[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 16 + (r ^ g)];
+        for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 17 + r];
         dft16<+1>(a);
         float2* e = ex + (g * 16) * 16 + r;
         e[0] = a[0];
@@ -1154,8 +1155,8 @@ fused_wide2_kernel(const FusedParams prm) {
 }
 
 // ---------------------------------------------------------------------------- full spectrum
-// smem: Yf[4096] | ex[4096] | A[4096] | ids[64] | nmu[64]
-constexpr size_t kFullSmem = sizeof(float2) * 3 * 4096 + sizeof(int) * 2 * kMaxFullScales;
+// smem: Yf[4096] | ex[4096] | A[256 x 17] | ids[64] | nmu[64]
+constexpr size_t kFullSmem = sizeof(float2) * (2 * 4096 + kTileA) + sizeof(int) * 2 * kMaxFullScales;
 
 // radix-16 over the aliases m' + 256 mu of spectrum bin m' = tid, pruned to the first NMU
 // aliases (the others are empty for a filter that occupies only NMU blocks of 256 bins)
@@ -1170,7 +1171,7 @@ __device__ __forceinline__ void full_prepass(const float2* __restrict__ Yf, cons
         a[k] = (k < NMU) ? cmul(Yf[tid + 256 * k], __ldg(tab + 256 * k)) : make_float2(0.f, 0.f);
     dft16<+1>(a);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) A[tid * 16 + (k ^ (tid & 15))] = k ? cmul(a[k], tw4k[k]) : a[k];
+    for (int k = 0; k < 16; ++k) A[tid * 17 + k] = k ? cmul(a[k], tw4k[k]) : a[k];
 }
 
 template <typename TIn, int KIND>
@@ -1180,7 +1181,7 @@ fused_full_kernel(const FusedParams prm) {
     float2* Yf = (float2*)smem_raw;      // order matters: the forward FFT's padded pass spills 2 KB into ex
     float2* ex = Yf + kFullN;
     float2* A = ex + kFullN;
-    int* s_ids = (int*)(A + kFullN);
+    int* s_ids = (int*)(A + kTileA);
     int* s_nmu = s_ids + kMaxFullScales;
 
     const int tid = threadIdx.x;
@@ -1239,7 +1240,7 @@ fused_full_kernel(const FusedParams prm) {
         __syncthreads();
         // pass 1 of the 256-point transforms (16 columns)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 16 + (r ^ g)];
+        for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 17 + r];
         dft16<+1>(a);
         float2* e = ex + (g * 16) * 16 + r;
         e[0] = a[0];
