@@ -325,7 +325,6 @@ int fast_plan_build(gcwt_plan* p) {
             }
             class_geometry(fc);
             if (fc.hop <= 0) { set_error("planner: non-positive hop"); return GCWT_ERR_ARG; }
-#ifndef GCWT_NO_WIDE2
             if (fc.wide) {                                        // same margins on the 2x longer chunk
                 const int64_t d = int64_t(1) << level, align = std::max<int64_t>(d, 16), nc2 = 2 * fc.nc_full;
                 const int64_t lead = (int64_t)(kWideT / 2 - 1) << fc.log2u, tail = (int64_t)(kWideT / 2 + 1) << fc.log2u;
@@ -353,7 +352,6 @@ int fast_plan_build(gcwt_plan* p) {
                 GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_table2, sizeof(float2) * tab2.size()));
                 GCWT_CUDA_OK(cudaMemcpy(fc.d_table2, tab2.data(), sizeof(float2) * tab2.size(), cudaMemcpyHostToDevice));
             }
-#endif
             const int nb = level >= 0 ? kBins : kFullN;
             const int ns = (int)fc.scale_ids.size();
             std::vector<float2> tab((size_t)ns * nb);
@@ -764,8 +762,7 @@ fused_banded_kernel(const FusedParams prm) {
 // moves these classes from the FP32-issue bound to the HBM bound.
 // smem: ex[4096] float2 | Zs[kMaxClassScales][256] float2 | Pc[2][kPcStride] float
 constexpr int kPcStride = kCoarse + 16;           // % 32 == 16: the two scales of a pair hit different banks
-constexpr int kPcStrideW = kCoarseWide + 40;      // % 32 == 8: the four scales of a quad hit different banks
-constexpr int kPcFloats = (2 * kPcStride > 4 * kPcStrideW) ? 2 * kPcStride : 4 * kPcStrideW;
+constexpr int kPcFloats = 2 * kPcStride;
 constexpr size_t kInterpSmem = sizeof(float2) * (4096 + kMaxClassScales * kBins) + sizeof(float) * kPcFloats + sizeof(int) * kMaxClassScales;
 
 template <int KIND, int LU, int T>   // LU > 0: compile-time log2 of the coarse spacing (store offsets become immediates); T taps
@@ -863,7 +860,7 @@ __device__ __forceinline__ void interp_rows_small(const float* __restrict__ pc, 
 // all U phases from one register window, taps from the constant bank, 128-bit stores.
 template <int KIND, int LU>
 __device__ __forceinline__ void interp_rows_wide(const float* __restrict__ pc, float* __restrict__ row,
-                                                 int ia, int ib, int own_hi) {
+                                                 int ia, int ib, int own_hi, bool aligned) {
     constexpr int U = 1 << LU;
     constexpr int COFF = (LU == 2) ? 0 : 4 * kWideT;
     for (int iota = ia + (int)threadIdx.x; iota < ib; iota += 256) {
@@ -880,7 +877,7 @@ __device__ __forceinline__ void interp_rows_wide(const float* __restrict__ pc, f
             o[phi] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_abs_approx(acc) : fmaxf(acc, 0.f);
         }
         float* op = row + (int64_t)iota * U;
-        if ((iota + 1) * U <= own_hi) {
+        if (aligned && (iota + 1) * U <= own_hi) {                // rows 16-byte aligned: 128-bit stores
 #pragma unroll
             for (int v = 0; v < U / 4; ++v) ((float4*)op)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
         } else {
@@ -890,7 +887,7 @@ __device__ __forceinline__ void interp_rows_wide(const float* __restrict__ pc, f
     }
 }
 
-template <int KIND, bool WIDE>     // WIDE: 4 coarse columns (U = D), four scales per pass
+template <int KIND>
 __global__ void __launch_bounds__(256, GCWT_INTERP_CTAS)
 fused_interp_kernel(const FusedParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -898,9 +895,9 @@ fused_interp_kernel(const FusedParams prm) {
     float2* Zs = ex + 4096;
     float* Pc = (float*)(Zs + kMaxClassScales * kBins);
     int* s_ids = (int*)(Pc + kPcFloats);
-    constexpr int NCOL = WIDE ? 4 : 8;             // coarse columns per chunk
+    constexpr int NCOL = 8;                        // coarse columns per chunk
     constexpr int NSC = 16 / NCOL;                 // scales transformed per 16-lane pass
-    constexpr int PCS = WIDE ? kPcStrideW : kPcStride;
+    constexpr int PCS = kPcStride;
 
     const int tid = threadIdx.x;
     if (tid < prm.n_scales) s_ids[tid] = prm.scale_ids[tid];
@@ -951,7 +948,7 @@ fused_interp_kernel(const FusedParams prm) {
 
     // taps of this thread's phase (one phase per thread while U <= 256): fetched once per block
     float c0[kInterpT];
-    if (!WIDE && lu >= 3 && lu <= 8) {
+    if (lu >= 3 && lu <= 8) {
         const int phi0 = tid & ((1 << lu) - 1);
 #pragma unroll
         for (int t = 0; t < kInterpT; ++t) c0[t] = __ldg(prm.coef + phi0 * kInterpT + t);
@@ -987,11 +984,7 @@ fused_interp_kernel(const FusedParams prm) {
         for (int sl = 0; sl < nsc; ++sl) {
             const float* pcs = Pc + sl * PCS;
             float* row = out_c + (int64_t)s_ids[pair + sl] * prm.s_stride;
-            if (WIDE) {
-                // (the sliding-window form measured slower here: 12 taps, 4 or 8 lanes per interval)
-                if (lu == 2) interp_rows_wide<KIND, 2>(pcs, row, ia, ib, own_hi);
-                else interp_rows_wide<KIND, 3>(pcs, row, ia, ib, own_hi);
-            } else if (lu == 2) {
+            if (lu == 2) {
                 interp_rows_small<KIND, 2>(pcs, row, ia, ib, own_hi);
             } else if (lu == 1) {
                 interp_rows_small<KIND, 1>(pcs, row, ia, ib, own_hi);
@@ -1102,6 +1095,7 @@ fused_wide2_kernel(const FusedParams prm) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) tw2k[k] = tw_pos(prm.twf, 2 * tid * k);        // e^{2 pi i m' k / 2048}
     float* const out_c = (float*)prm.out + c * prm.c_stride + t0;
+    const bool aligned = prm.iters != 0;                           // rows 16-byte aligned: 128-bit stores allowed
     float2* const A = B1;
     float2* const ex = B0;
     float* const Pc = (float*)B1;
@@ -1147,8 +1141,8 @@ fused_wide2_kernel(const FusedParams prm) {
         for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl) {
             const float* pcs = Pc + sl * kPcStride;
             float* row = out_c + (int64_t)s_ids[pair + sl] * prm.s_stride;
-            if (lu == 2) interp_rows_wide<KIND, 2>(pcs, row, ia, ib, own_hi);
-            else interp_rows_wide<KIND, 3>(pcs, row, ia, ib, own_hi);
+            if (lu == 2) interp_rows_wide<KIND, 2>(pcs, row, ia, ib, own_hi, aligned);
+            else interp_rows_wide<KIND, 3>(pcs, row, ia, ib, own_hi, aligned);
         }
         __syncthreads();
     }
@@ -1343,11 +1337,13 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
     GCWT_CUDA_OK(cudaGetLastError());
 
     // ---- fused kernels ---------------------------------------------------------------
-    // the thread <-> interval interpolators (U = 2, 4 and the wide classes) write 128-bit vectors:
+    // the thread <-> interval interpolators of fused_interp_kernel (U = 2, 4) write 128-bit vectors:
     // rows must be 16-byte aligned, else the class falls back to the direct kernel
     const bool rows_aligned = ((uintptr_t)out % 16 == 0) && (s_stride % 4 == 0) && (c_stride % 4 == 0);
     auto uses_interp = [&](const FastClass& fc) {
-        return fc.level >= 0 && fc.interp && ((fc.log2u >= 3 && !fc.wide) || rows_aligned);
+        if (fc.level < 0 || !fc.interp) return false;
+        if (fc.wide && fc.d_table2) return true;                  // fused_wide2_kernel stores scalars when it must
+        return (fc.log2u >= 3 && !fc.wide) || rows_aligned;
     };
     auto launch_class = [&](const FastClass& fc, cudaStream_t cs, bool own_span) -> int {
         const int sp = own_span ? prof_begin(p, fc.level < 0 ? 1 : (fc.interp ? 4 : 2), cs, fc.level + 2) : -1;
@@ -1362,14 +1358,15 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prm.out = out; prm.s_stride = s_stride; prm.c_stride = c_stride;
         prm.inv_nc = 1.0f / (float)fc.nc_full;
         prm.log2u = fc.log2u; prm.coef = fc.d_coef; prm.twf = p->d_twiddle; prm.scale_nmu = fc.d_scale_nmu;
-        if (uses_interp(fc) && fc.wide && fc.d_table2) {
+        if (fc.level >= 0 && fc.interp && fc.wide && fc.d_table2) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
             prm.log2d = fc.level;
             prm.offset = fc.offset2; prm.hop = fc.hop2;
             prm.n_chunks = (n + fc.hop2 - 1) / fc.hop2;
             prm.table = fc.d_table2;
-            prm.p_cols = 8; prm.log2p = 3; prm.iters = 1; prm.units_per_chunk = 1;
+            prm.p_cols = 8; prm.log2p = 3; prm.units_per_chunk = 1;
+            prm.iters = rows_aligned ? 1 : 0;                      // 128-bit stores allowed
             const int64_t nblk = n_channels * prm.n_chunks;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
             if (p->out_kind == GCWT_OUT_AMPLITUDE)
@@ -1377,7 +1374,6 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             else
                 fused_wide2_kernel<GCWT_OUT_POWER><<<(unsigned)nblk, 256, kWide2Smem, cs>>>(prm);
         } else if (uses_interp(fc)) {
-            // (an unaligned wide class falls through to the direct kernel with its own geometry)
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
             prm.log2d = fc.level;
@@ -1394,15 +1390,10 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.units_per_chunk = (int)splits;
             const int64_t nblk = chunks * splits;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
-            if (fc.wide) {
-                if (p->out_kind == GCWT_OUT_AMPLITUDE)
-                    fused_interp_kernel<GCWT_OUT_AMPLITUDE, true><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
-                else
-                    fused_interp_kernel<GCWT_OUT_POWER, true><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
-            } else if (p->out_kind == GCWT_OUT_AMPLITUDE)
-                fused_interp_kernel<GCWT_OUT_AMPLITUDE, false><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
+            if (p->out_kind == GCWT_OUT_AMPLITUDE)
+                fused_interp_kernel<GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
             else
-                fused_interp_kernel<GCWT_OUT_POWER, false><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
+                fused_interp_kernel<GCWT_OUT_POWER><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
         } else if (fc.level >= 0) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1477,10 +1468,8 @@ static bool g_attr_done[64] = {false};
 
 template <typename TIn>
 static int set_smem_attrs() {
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_wide2_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWide2Smem));
     GCWT_CUDA_OK(cudaFuncSetAttribute(fused_wide2_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWide2Smem));
     return GCWT_OK;

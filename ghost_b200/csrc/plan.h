@@ -29,7 +29,6 @@ constexpr int kInterpMinLevel = 3;  // interpolated classes: coarse spacing U = 
 constexpr int kCoarse = 2048;       // coarse |W|^2 samples per chunk and scale (8 columns x 256)
 constexpr int kWideT = GCWT_WIDE_T;          // taps of the interpolator of the wide-spacing classes (U = D)
 constexpr int kWideMaxLevel = 3;    // levels 2 and 3 use U = D when their bands allow it
-constexpr int kCoarseWide = 1024;   // coarse samples per chunk and scale in those classes (4 columns x 256)
 constexpr double kInterpMinOs = 4.0; // |W|^2 over-sampling guaranteed on the grid U = D/2 (band <= kBins bins)
 constexpr double kWideMinOs = 2.5;   // over-sampling required of a class before it may use U = D
 constexpr int kHalfbandT = 19;      // half-band taps run from -T..T
