@@ -16,6 +16,11 @@
 // times the phase ramp e^{2 pi i m n2 / (256 P)}.  Each lane of a warp owns one column
 // n2, so stores are contiguous runs across lanes.
 //
+// Kernels: pyramid_kernel (decimation), fused_full_kernel (full rate, 4096-point chunks),
+// fused_banded_kernel (exact pruned inverse, any output kind), and for amplitude / power the two
+// coarse-grid + interpolation kernels fused_interp_kernel (U = D/2, 8 least-squares taps) and
+// fused_wide2_kernel (levels 2-3, U = D, 12 taps, 2048-sample chunks with the spectrum in registers).
+//
 // Replaces ghost/sigtools/convolution.py:63-87 (fastconv overlap-add), morseutils.py:
 // 115-151 (kernel synthesis) and transforms.py:142-143,202-204 (mean removal, abs).
 #include "plan.h"
@@ -196,7 +201,7 @@ static void class_geometry(FastClass& fc) {
 // filters' measured band width), so each phase is the least-squares fit of a fractional delay over
 // exactly that band: c = A^-1 b with A[t][t'] = sinc(2 fmax (d_t - d_t')), b[t] = sinc(2 fmax d_t),
 // d_t = tap position relative to the output.  Worst-case error over ALL tones in the band (not
-// just typical spectra): 8 taps 3e-6 at os = 4 and 6e-7 at os = 5; 14 taps 2e-7 at os = 2.5 --
+// just typical spectra): 8 taps 2.5e-6 at os = 4 and 4e-7 at os = 5; 12 taps 1.5e-6 at os = 2.5 --
 // two orders of magnitude below a Kaiser-windowed sinc of the same length.
 static long double sinc_pi(long double x) {
     const long double pi = 3.14159265358979323846264338327950288L;
