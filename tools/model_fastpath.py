@@ -207,3 +207,34 @@ def fast_cwt(x, scales, tol=3e-7, nc_dec=1024, full_n=4096, dtype=np.float64, h=
                 out[i, lo:hi] = v[lo - t0:hi - t0]
             q += 1
     return out
+
+
+# ---------------------------------------------------------------- coarse grid + interpolation
+def interp_taps(log2u, n_taps, oversampling):
+    """Taps of the device's polyphase interpolator, from the library's host-only entry point."""
+    import ctypes as C
+    from ghost_b200 import _lib
+    U = 1 << log2u
+    taps = np.zeros((U, n_taps), dtype=np.float32)
+    rc = _lib.load().gcwt_interp_taps(log2u, n_taps, float(oversampling), taps.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc != 0:
+        raise RuntimeError("gcwt_interp_taps failed")
+    return taps
+
+
+def interpolate_power(power_full, log2u, taps):
+    """What the amplitude / power kernels do with |W|^2: keep it on the grid n = iota * U only and
+    bring it back to the full rate with the polyphase taps (output iota * U + phi =
+    sum_t taps[phi][t] * p[iota + t - (T/2 - 1)]).  Returns the re-interpolated |W|^2."""
+    U, T = taps.shape
+    n = len(power_full)
+    p = power_full[::U].astype(np.float64)
+    pad = np.concatenate([np.zeros(T), p, np.zeros(T)])
+    out = np.zeros(len(p) * U)
+    idx = np.arange(len(p))
+    for phi in range(U):
+        acc = np.zeros(len(p))
+        for t in range(T):
+            acc += float(taps[phi, t]) * pad[T + idx + t - (T // 2 - 1)]
+        out[phi::U] = acc
+    return np.maximum(out[:n], 0.0)
