@@ -151,6 +151,8 @@ def run_reference(args):
     if rank != 0:
         return
     wl = dict(WORKLOADS[args.workload])
+    if args.samples:
+        wl["n"] = int(args.samples)
     freqs = plan_frequencies(wl)
     from multiprocessing import cpu_count
     from ghost_b200 import synth
