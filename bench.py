@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=None, help="override samples per channel")
     ap.add_argument("--channels", type=int, default=None, help="channels per GPU (default: workload's)")
     ap.add_argument("--tile", type=int, default=None, help="samples per time tile (tiled workloads)")
+    ap.add_argument("--no-guard", action="store_true", help="plan without the execute-time accuracy guard")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
@@ -207,7 +208,7 @@ def run_ours(args):
     om = freqs / (fs / 2.0) * np.pi
     L = m.compute_lengths(om)
     k0, nt, terms = scale_tables(m, om, L)
-    plan = CwtPlan(L, k0, nt, terms, dtype=np.float32, output=wl["output"], device=local)
+    plan = CwtPlan(L, k0, nt, terms, dtype=np.float32, output=wl["output"], device=local, guard=not args.no_guard)
     S = len(freqs)
 
     # synthetic channels of this rank (channel shard: rank r owns channels r*nch .. r*nch+nch-1);
@@ -269,6 +270,7 @@ def run_ours(args):
         print("rank %d host ms per step (launch side): %s; device total %.1f ms" % (
             rank, ["%.1f" % (t * 1e3) for t in step_wall], ms_total), file=sys.stderr, flush=True)
     launches = _lib.launch_count()
+    gstats = plan.guard_stats()
     prof = plan.profile_read(reset=True)
     plan.profile(False)
     if world > 1:
@@ -357,6 +359,8 @@ def run_ours(args):
                        "scale_classes": {"band_limited_interpolated": n_interp, "band_limited": n_banded,
                                          "full_spectrum": n_full, "generic": int((levels == -2).sum())}},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "guard": {"enabled": not args.no_guard, "pairs_checked": gstats["checked"],
+                      "pairs_recomputed_fp64": gstats["total"]},
             "clocks": sampler.summary(),
         }
         print(json.dumps(line))

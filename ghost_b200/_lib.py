@@ -16,6 +16,7 @@ F32, F64 = 0, 1
 OUT_COMPLEX, OUT_AMPLITUDE, OUT_POWER = 0, 1, 2
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_INTERP = 2
+FLAG_NO_GUARD = 4
 
 EXPORTS = (
     "gcwt_version", "gcwt_last_error", "gcwt_launch_count", "gcwt_plan_create",
@@ -23,6 +24,7 @@ EXPORTS = (
     "gcwt_channel_means", "gcwt_execute", "gcwt_execute_host", "gcwt_filter_response",
     "gcwt_morse_kernel", "gcwt_profile_enable", "gcwt_profile_read",
     "gcwt_fastconv", "gcwt_dft", "gcwt_analytic_signal", "gcwt_moments", "gcwt_interp_taps",
+    "gcwt_guard_stats",
 )
 
 
@@ -42,6 +44,7 @@ class PlanDesc(C.Structure):
         ("device", C.c_int32),
         ("flags", C.c_int32),
         ("band_tol", C.c_double),
+        ("guard_tol", C.c_double),
     ]
 
 
@@ -78,6 +81,7 @@ def load():
     lib.gcwt_analytic_signal.argtypes = [dp, i64, dp, i32]
     lib.gcwt_moments.argtypes = [vp, i32, i64, i32, dp, i32, vp]
     lib.gcwt_interp_taps.argtypes = [i32, i32, C.c_double, C.POINTER(C.c_float)]
+    lib.gcwt_guard_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_ubyte)]
     lib.gcwt_profile_enable.argtypes = [vp, i32]
     lib.gcwt_profile_read.argtypes = [vp, dp, C.POINTER(i64), i32]
     _lib = lib

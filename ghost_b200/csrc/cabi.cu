@@ -131,6 +131,8 @@ int gcwt_plan_create(gcwt_plan** out, const gcwt_plan_desc* d) {
     p->device = d->device;
     p->flags = d->flags;
     p->band_tol = d->band_tol > 0 ? d->band_tol : 3e-7;
+    p->guard_tol = d->guard_tol > 0 ? d->guard_tol : 5e-6;
+    p->guard = d->compute_type == GCWT_F32 && !(d->flags & (GCWT_FLAG_NO_GUARD | GCWT_FLAG_FORCE_GENERIC));
     int off = 0;
     for (int s = 0; s < d->n_scales; ++s) {
         ScaleInfo sc;
@@ -221,6 +223,17 @@ int gcwt_plan_levels(const gcwt_plan* p, int32_t* levels_out) {
 
 size_t gcwt_plan_workspace_bytes(const gcwt_plan* p) { return p ? p->ws.bytes : 0; }
 
+int gcwt_guard_stats(const gcwt_plan* p, int64_t* last_pairs, int64_t* total_pairs, int64_t* checked_pairs,
+                     unsigned char* scale_flags) {
+    if (!p) { set_error("guard_stats: NULL plan"); return GCWT_ERR_ARG; }
+    if (last_pairs) *last_pairs = p->guard_last;
+    if (total_pairs) *total_pairs = p->guard_total;
+    if (checked_pairs) *checked_pairs = p->guard_checked;
+    if (scale_flags)
+        for (int s = 0; s < p->n_scales; ++s) scale_flags[s] = (size_t)s < p->guard_last_flags.size() ? p->guard_last_flags[s] : 0;
+    return GCWT_OK;
+}
+
 int gcwt_channel_means(const void* x, int32_t in_type, int64_t n_channels, int64_t n_samples,
                        int64_t x_stride, double* means_dev, int32_t device, void* stream) {
     if (!x || !means_dev) { set_error("channel_means: NULL argument"); return GCWT_ERR_ARG; }
@@ -271,6 +284,10 @@ int gcwt_execute(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_channel
     if (p->compute_type == GCWT_F32 && !p->classes.empty()) {
         rc = fast_execute(p, x, in_type, n_channels, n_samples, x_stride, halo_left, halo_right, d_means,
                           out, out_scale_stride, out_channel_stride, st);
+        if (rc) return rc;
+        // accuracy guard: waits for the verdict of this call and re-computes the failing pairs in fp64
+        rc = guard_resolve(p, x, in_type, n_channels, n_samples, x_stride, halo_left, halo_right, d_means,
+                           out, out_scale_stride, out_channel_stride, st);
         if (rc) return rc;
         if (!p->generic_ids.empty()) GCWT_CUDA_OK(cudaStreamSynchronize(st));
     }

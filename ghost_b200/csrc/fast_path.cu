@@ -28,6 +28,7 @@
 #include "multiplier.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <type_traits>
@@ -73,6 +74,19 @@ static void design_halfband(double* odd /*kHalfbandOdd*/) {
         sum += 2.0 * odd[k];
     }
     for (int k = 0; k < kHalfbandOdd; ++k) odd[k] *= 0.5 / sum;      // unit DC gain
+    // The device applies the taps in fp32.  Plain rounding leaves sum(odd) - 0.25 ~ 1e-8, i.e. a gain of
+    // ~2e-8 at the input Nyquist frequency instead of the exact zero a half-band filter has there -- the
+    // floor of the alias rejection of every stage but the last two.  Round greedily instead, largest
+    // tap first, each one absorbing what the previous roundings left: the fp32 taps then sum to 0.25 to
+    // ~1e-14 and the response near Nyquist is again quadratic in the distance from it.
+    long double done = 0.0L;
+    for (int k = 0; k < kHalfbandOdd; ++k) {
+        long double rest = 0.0L;
+        for (int j = k + 1; j < kHalfbandOdd; ++j) rest += (long double)odd[j];
+        const float f = (float)(0.25L - done - rest);
+        odd[k] = (double)f;
+        done += (long double)f;
+    }
 }
 
 static double halfband_gain(const double* odd, double theta) {
@@ -276,6 +290,159 @@ static int upload_constants(const gcwt_plan* p) {
     return GCWT_OK;
 }
 
+// ---- accuracy guard: plan-time error gains -----------------------------------------------------
+// For a scale served at decimation level l (D = 2^l) the fused path's response differs from the exact
+// filter H only outside the kept band [0, pi / (2D)):
+//   alias: a component at w = (2 pi k + theta_m) / D, k != 0, reaches bin m of the level's grid with the
+//          pyramid gain g(k, m) = prod_i |hb((2 pi (k mod 2^i) + theta_m) / 2^i)|, i = 1..l, and is then
+//          multiplied by the table entry T[m] = |G[m]| / Hdec[m];
+//   drop:  the response H(w) itself, which the path treats as zero there (and at all negative frequencies).
+// Both are reduced to one gain per octave b (|w| in (pi / 2^(b+1), pi / 2^b]) so that the execute-time
+// check is  sum_b gain[b] * E_b  <=  tol^2 * (measured output energy), with E_b from the pyramid.
+struct HbTaps { double odd[kHalfbandOdd]; };
+
+__device__ __forceinline__ double hb_gain_dev(const HbTaps& h, double theta) {
+    double g = 0.5;
+#pragma unroll
+    for (int k = 0; k < kHalfbandOdd; ++k) g += 2.0 * h.odd[k] * cos((double)(2 * k + 1) * theta);
+    return g;
+}
+
+__global__ void guard_alias_kernel(int level, HbTaps h, unsigned* __restrict__ B /*[kGuardSlots][kBins] float bits*/) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int D = 1 << level;
+    if (idx >= (int64_t)D * kBins) return;
+    const int k = (int)(idx / kBins), m = (int)(idx % kBins);
+    if (k == 0) return;                                           // k = 0 is the kept band itself
+    const double two_pi = 6.283185307179586476925287;
+    const double theta_m = two_pi * (double)m / (double)kChunkDec;
+    double g = 1.0;
+    for (int i = 1; i <= level; ++i) {
+        const int r = k & ((1 << i) - 1);
+        g *= fabs(hb_gain_dev(h, (two_pi * (double)r + theta_m) / (double)(1 << i)));
+    }
+    const int kk = min(k, D - k);                                 // |w| ~ 2 pi kk / D
+    int b = 0;
+    while (((int64_t)kk << (b + 2)) <= D) ++b;                    // 2 kk / D in (2^-(b+1), 2^-b]
+    atomicMax(B + b * kBins + m, __float_as_uint((float)g));
+}
+
+__global__ void __launch_bounds__(256)
+guard_drop_kernel(const ScaleInfo* __restrict__ scales, const double* __restrict__ terms, float* __restrict__ out) {
+    __shared__ unsigned mx[kGuardSlots];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const ScaleInfo sc = scales[s];
+    if (tid < kGuardSlots) mx[tid] = 0u;
+    __syncthreads();
+    const int lev = sc.level;
+    if (lev >= kMinFastLevel) {
+        const double* X = terms + sc.term_off;
+        const double pi = 3.141592653589793238462643;
+        // octave b = lev, positive side: the exact response on a 4x finer grid than the chunk's (>= 8
+        // samples per side lobe), bins just above the kept band
+        const int64_t n = (int64_t)(4 * kChunkDec) << lev;
+        for (int i = tid; i < 4 * kBins; i += 256) {
+            const double g = fabs(morse_response(4 * kBins + i, n, sc.L, sc.k_first, sc.n_terms, X));
+            atomicMax(&mx[lev], __float_as_uint((float)(1.1 * g)));
+        }
+        // everywhere else the envelope of the side lobes, |sum_k (-1)^k X_k / sin((w - w_k) / 2)| / L, at
+        // 24 log-spaced points per octave and sign; slot lev + 1 = negative frequencies below the band edge
+        for (int i = tid; i < (lev + 2) * 48; i += 256) {
+            const int b = i / 48, j = i % 48, t = j % 24;
+            const bool neg = j >= 24;
+            if (!neg && b >= lev) continue;
+            double lo = pi / (double)(int64_t(1) << (b + 1)), hi = 2.0 * lo;
+            if (b == lev + 1) { hi = pi / (double)(int64_t(2) << lev); lo = hi / 64.0; }
+            const double w = (neg ? -1.0 : 1.0) * lo * pow(hi / lo, (double)t / 23.0);
+            const double step = 2.0 * pi / (double)sc.L;
+            double far = 0.0, near = 0.0;
+            for (int q = 0; q < sc.n_terms; ++q) {
+                const int64_t k = sc.k_first + q;
+                const double d = w - step * (double)k;
+                if (fabs(d) < step) near += X[q];                  // within one grid spacing: at most X_k
+                else far += ((k & 1) ? -X[q] : X[q]) / sin(0.5 * d);
+            }
+            const double v = 1.15 * (fabs(far) / (double)sc.L + near);
+            atomicMax(&mx[b], __float_as_uint((float)v));
+        }
+    }
+    __syncthreads();
+    if (tid < kGuardSlots) out[(int64_t)s * kGuardSlots + tid] = __uint_as_float(mx[tid]);
+}
+
+static int guard_plan_build(gcwt_plan* p, const PlanResponses& pr, const std::vector<double>& hb) {
+    const int S = p->n_scales;
+    std::vector<float> gain((size_t)S * kGuardSlots, 0.f), q(S, 0.f);
+    std::vector<int32_t> cls(S, -1);
+    for (size_t ci = 0; ci < p->classes.size(); ++ci)
+        for (int id : p->classes[ci].scale_ids) cls[id] = (int32_t)ci;
+    // side-lobe gains (device, needs the levels chosen by the planner)
+    GCWT_CUDA_OK(cudaMemcpy(p->d_scales, p->scales.data(), sizeof(ScaleInfo) * S, cudaMemcpyHostToDevice));
+    float* d_drop = nullptr;
+    GCWT_CUDA_OK(cudaMalloc((void**)&d_drop, sizeof(float) * S * kGuardSlots));
+    guard_drop_kernel<<<S, 256>>>(p->d_scales, p->d_terms, d_drop);
+    count_launch();
+    std::vector<float> drop((size_t)S * kGuardSlots);
+    cudaError_t e = cudaMemcpy(drop.data(), d_drop, sizeof(float) * drop.size(), cudaMemcpyDeviceToHost);
+    cudaFree(d_drop);
+    if (e != cudaSuccess) { set_error(std::string("guard tables: ") + cudaGetErrorString(e)); return GCWT_ERR_CUDA; }
+    // pyramid alias gains, one table per level in use
+    HbTaps taps;
+    for (int k = 0; k < kHalfbandOdd; ++k) taps.odd[k] = (double)(float)p->halfband_odd[k];
+    std::map<int, std::vector<float>> alias;
+    for (const FastClass& fc : p->classes) {
+        if (fc.level < kMinFastLevel || alias.count(fc.level)) continue;
+        unsigned* d_b = nullptr;
+        GCWT_CUDA_OK(cudaMalloc((void**)&d_b, sizeof(unsigned) * kGuardSlots * kBins));
+        GCWT_CUDA_OK(cudaMemset(d_b, 0, sizeof(unsigned) * kGuardSlots * kBins));
+        const int64_t total = (int64_t)kBins << fc.level;
+        guard_alias_kernel<<<(unsigned)((total + 255) / 256), 256>>>(fc.level, taps, d_b);
+        count_launch();
+        std::vector<float>& B = alias[fc.level];
+        B.resize((size_t)kGuardSlots * kBins);
+        e = cudaMemcpy(B.data(), d_b, sizeof(float) * B.size(), cudaMemcpyDeviceToHost);
+        cudaFree(d_b);
+        if (e != cudaSuccess) { set_error(std::string("guard tables: ") + cudaGetErrorString(e)); return GCWT_ERR_CUDA; }
+    }
+    for (int s = 0; s < S; ++s) {
+        const int lev = p->scales[s].level;
+        if (cls[s] < 0) continue;
+        if (lev < 0) {                                             // full-spectrum class: rounding only
+            const double* g = pr.full(s);
+            double acc = 0.0;
+            for (int m = 0; m < kFullN; ++m) acc += g[m] * g[m];
+            q[s] = (float)(acc / kFullN);
+            continue;
+        }
+        const double* g = pr.level(s, lev);
+        const std::vector<float>& B = alias[lev];
+        double T[kBins], acc = 0.0;
+        for (int m = 0; m < kBins; ++m) {
+            double t = std::fabs(g[m]);
+            for (int j = 1; j <= lev; ++j) t /= hb[(size_t)j * kBins + m];
+            T[m] = t;
+            acc += t * t;
+        }
+        q[s] = (float)(acc / kChunkDec);
+        for (int b = 0; b <= lev + 1 && b < kGuardSlots; ++b) {
+            double al = 0.0;
+            if (b < lev)
+                for (int m = 0; m < kBins; ++m) al = std::max(al, (double)B[(size_t)b * kBins + m] * T[m]);
+            const double tot = al + (double)drop[(size_t)s * kGuardSlots + b];
+            gain[(size_t)s * kGuardSlots + b] = (float)(tot * tot);
+        }
+    }
+    GCWT_CUDA_OK(cudaMalloc((void**)&p->d_guard_gain, sizeof(float) * gain.size()));
+    GCWT_CUDA_OK(cudaMalloc((void**)&p->d_guard_q, sizeof(float) * S));
+    GCWT_CUDA_OK(cudaMalloc((void**)&p->d_guard_class, sizeof(int32_t) * S));
+    GCWT_CUDA_OK(cudaMemcpy(p->d_guard_gain, gain.data(), sizeof(float) * gain.size(), cudaMemcpyHostToDevice));
+    GCWT_CUDA_OK(cudaMemcpy(p->d_guard_q, q.data(), sizeof(float) * S, cudaMemcpyHostToDevice));
+    GCWT_CUDA_OK(cudaMemcpy(p->d_guard_class, cls.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice));
+    GCWT_CUDA_OK(cudaEventCreateWithFlags(&p->ev_guard, cudaEventDisableTiming));
+    p->guard_last_flags.assign(S, 0);
+    return GCWT_OK;
+}
+
 int fast_plan_build(gcwt_plan* p) {
     design_halfband(p->halfband_odd);
     { int rc = upload_constants(p); if (rc) return rc; }
@@ -404,10 +571,26 @@ int fast_plan_build(gcwt_plan* p) {
             p->classes.push_back(fc);
         }
     }
+    if (p->guard && !p->classes.empty()) {
+        if (p->max_level + 2 >= kGuardLevels || (int)p->classes.size() > 64) p->guard = false;   // cannot happen (kMaxFastLevel = 14)
+        else { int rc = guard_plan_build(p, pr, hb); if (rc) return rc; }
+    } else {
+        p->guard = false;
+    }
     return GCWT_OK;
 }
 
 void fast_plan_free(gcwt_plan* p) {
+    if (p->d_guard_gain) cudaFree(p->d_guard_gain);
+    if (p->d_guard_q) cudaFree(p->d_guard_q);
+    if (p->d_guard_class) cudaFree(p->d_guard_class);
+    if (p->d_guard_acc) cudaFree(p->d_guard_acc);
+    if (p->d_guard_pow) cudaFree(p->d_guard_pow);
+    if (p->d_guard_flags) cudaFree(p->d_guard_flags);
+    if (p->h_guard_flags) cudaFreeHost(p->h_guard_flags);
+    if (p->ev_guard) cudaEventDestroy(p->ev_guard);
+    p->d_guard_gain = p->d_guard_q = nullptr; p->d_guard_class = nullptr; p->d_guard_acc = nullptr;
+    p->d_guard_pow = nullptr; p->d_guard_flags = p->h_guard_flags = nullptr; p->ev_guard = nullptr;
     for (auto& fc : p->classes) {
         if (fc.d_table) cudaFree(fc.d_table);
         if (fc.d_table2) cudaFree(fc.d_table2);
@@ -427,13 +610,16 @@ template <typename TIn, bool FIRST>
 __global__ void __launch_bounds__(256)
 pyramid_kernel(const TIn* __restrict__ in, int64_t in_stride, int64_t in_lo, int64_t in_hi,
                const double* __restrict__ means, float* __restrict__ out, int64_t out_stride,
-               int64_t out_lo, int64_t out_len) {
+               int64_t out_lo, int64_t out_len,
+               double* __restrict__ acc, int acc_stride, int level, int64_t seg_in, int64_t seg_out) {
     // The tile of 2*kPyrTile + 2T inputs is kept de-interleaved: ev[i] = input(u0 + 2i),
     // od[i] = input(u0 + 2i + 1), u0 = 2 i0 - T.  With T odd the centre of output j is od[j + kMid]
     // and its taps are ev[j + kMid - k], ev[j + kMid + 1 + k].  A thread owns outputs 4 tid .. 4 tid + 3:
     // with kMid = 9 its 23 even-phase inputs start at ev[4 tid] and its four centres at od[4 tid + 9],
     // so everything arrives as 128-bit shared-memory loads (od is stored shifted by kMid + 3 to line
     // up) -- 7 loads per 4 outputs instead of 21 per output -- and leaves as one 128-bit store.
+    // Guard (acc != nullptr): the energy of the owned outputs that lie inside the segment [0, seg_out) is
+    // added to acc[c][level]; the first level also adds the energy of its owned inputs to acc[c][0].
     static_assert(kHalfbandT == 19, "tile indexing below assumes kMid == 9");
     constexpr int kMid = (kHalfbandT - 1) / 2;
     constexpr int kEv = kPyrTile + 2 * kMid + 2 + 4;                // 4 tid + 23 <= kEv
@@ -457,36 +643,55 @@ pyramid_kernel(const TIn* __restrict__ in, int64_t in_stride, int64_t in_lo, int
         const int64_t u = u0 + k;
         raw[it] = (k < kIn && u >= in_lo && u < in_hi) ? src[u] : (TIn)0;
     }
+    float e_in = 0.f;
 #pragma unroll
     for (int it = 0; it < kRounds; ++it) {
         const int k = (int)threadIdx.x + 256 * it;
         const int64_t u = u0 + k;
         const float v = (u >= in_lo && u < in_hi) ? (FIRST ? (float)((TSub)raw[it] - mu) : (float)raw[it]) : 0.f;
         if (k < kIn) { if (k & 1) ods[(k >> 1) + kOdShift] = v; else ev[k >> 1] = v; }
+        if (FIRST && k >= kHalfbandT && k < kHalfbandT + 2 * kPyrTile && u >= 0 && u < seg_in) e_in = fmaf(v, v, e_in);
     }
     __syncthreads();
     const int j0 = 4 * threadIdx.x;
-    if (i0 + j0 - out_lo >= out_len) return;
-    float e[24];
+    const bool active = i0 + j0 - out_lo < out_len;
+    float e_out = 0.f;
+    if (active) {
+        float e[24];
 #pragma unroll
-    for (int v = 0; v < 6; ++v) {
-        const float4 t = *(const float4*)(ev + j0 + 4 * v);
-        e[4 * v] = t.x; e[4 * v + 1] = t.y; e[4 * v + 2] = t.z; e[4 * v + 3] = t.w;
+        for (int v = 0; v < 6; ++v) {
+            const float4 t = *(const float4*)(ev + j0 + 4 * v);
+            e[4 * v] = t.x; e[4 * v + 1] = t.y; e[4 * v + 2] = t.z; e[4 * v + 3] = t.w;
+        }
+        const float4 ctr = *(const float4*)(ods + j0 + 12);              // od[j0 + kMid .. + 3]
+        const float cv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            // fp32 accumulation, smallest taps first (fp64 would spend the kernel on conversions)
+            float a = 0.f;
+#pragma unroll
+            for (int k = kHalfbandOdd - 1; k >= 0; --k)
+                a = fmaf(c_halfband[k], e[q + kMid - k] + e[q + kMid + 1 + k], a);
+            o[q] = fmaf(0.5f, cv[q], a);
+            const int64_t io = i0 + j0 + q;
+            if (io >= 0 && io < seg_out) e_out = fmaf(o[q], o[q], e_out);
+        }
+        // rows are padded to a multiple of four floats: the last quad may spill into the padding
+        *(float4*)(out + (int64_t)c * out_stride + (i0 + j0 - out_lo)) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    const float4 ctr = *(const float4*)(ods + j0 + 12);              // od[j0 + kMid .. + 3]
-    const float cv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
-    float o[4];
+    if (acc != nullptr) {                                            // block-uniform
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        // fp32 accumulation, smallest taps first (fp64 would spend the kernel on conversions)
-        float acc = 0.f;
-#pragma unroll
-        for (int k = kHalfbandOdd - 1; k >= 0; --k)
-            acc = fmaf(c_halfband[k], e[q + kMid - k] + e[q + kMid + 1 + k], acc);
-        o[q] = fmaf(0.5f, cv[q], acc);
+        for (int o = 16; o > 0; o >>= 1) {
+            e_out += __shfl_xor_sync(0xffffffffu, e_out, o);
+            if (FIRST) e_in += __shfl_xor_sync(0xffffffffu, e_in, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            double* a = acc + (int64_t)c * acc_stride;
+            if (e_out != 0.f) atomicAdd(a + level, (double)e_out);
+            if (FIRST && e_in != 0.f) atomicAdd(a, (double)e_in);
+        }
     }
-    // rows are padded to a multiple of four floats: the last quad may spill into the padding
-    *(float4*)(out + (int64_t)c * out_stride + (i0 + j0 - out_lo)) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // ============================================================================ fused kernels
@@ -511,6 +716,14 @@ struct FusedParams {
     const float* coef;        // interp: float [U][kInterpT]
     const float2* twf;        // e^{-2 pi i k / 4096}
     const int32_t* scale_nmu; // full: occupied 256-bin blocks per scale
+    // accuracy guard (all null / zero when the guard is off)
+    double* acc;              // [channels][acc_stride]: e_0 .. e_(kGuardLevels-1), then one chunk energy per class
+    int acc_stride;
+    int class_idx;
+    float ech_weight;         // chunk energy -> full-rate-equivalent energy of the segment (D * hop / chunk)
+    float* pow;               // [channels][pow_stride] measured sum |W|^2 per scale
+    int pow_stride;
+    float pow_weight;         // full / banded kernels sample a fraction of their outputs
 };
 
 // e^{+2 pi i k / 4096} from the table of e^{-2 pi i k / 4096}
@@ -588,6 +801,46 @@ __device__ __forceinline__ float chunk_mean(const float* v, float* scratch) {
     return t * (1.0f / (float)(NV * 256));
 }
 
+// Guard: sum of squares of the chunk after its mean has been removed, reduced over the block and added
+// (by thread 0) to the class's chunk-energy accumulator of this channel.  `scratch` as in chunk_mean,
+// but the caller must place a barrier between the two uses.
+template <int NV>
+__device__ __forceinline__ void chunk_energy_add(const float* v, float cm, float* scratch, double* dst, float weight) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { const float d = v[k] - cm; s = fmaf(d, d, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();                                           // every thread has read the mean's partial sums
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += scratch[w];
+        atomicAdd(dst, (double)(t * weight));
+    }
+}
+
+// Guard: |W|^2 of the outputs a thread owns in one pass (bit k of `own`), reduced over the lanes that
+// share a scale (lanes differing in bit 3 hold different scales when PAIRED) into a shared counter.
+template <bool PAIRED>
+__device__ __forceinline__ void guard_pow_add(const float2* a, unsigned own, float* counter) {
+    float pw = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float v = a[k].x * a[k].x + a[k].y * a[k].y;
+        pw += (own >> k & 1u) ? v : 0.f;
+    }
+    pw += __shfl_xor_sync(0xffffffffu, pw, 16);
+    if (!PAIRED) pw += __shfl_xor_sync(0xffffffffu, pw, 8);
+    pw += __shfl_xor_sync(0xffffffffu, pw, 4);
+    pw += __shfl_xor_sync(0xffffffffu, pw, 2);
+    pw += __shfl_xor_sync(0xffffffffu, pw, 1);
+    const unsigned lane = threadIdx.x & 31u;
+    if ((lane & (PAIRED ? 23u : 31u)) == 0) atomicAdd(counter, pw);
+}
+
 // 1024-point forward FFT: five radix-4 Stockham passes, 256 threads, one butterfly per thread and
 // pass.  Thread j handles butterfly j in every pass, so all of its 12 twiddles are fetched up
 // front in one batch of independent loads (one memory latency instead of four in a chain).
@@ -663,7 +916,7 @@ __device__ __forceinline__ void smem_fft4096_forward(float2* x, float2* y, const
 
 // ---------------------------------------------------------------------------- banded
 // smem: ex[2][4096] | Zs[kMaxClassScales][256] | Estep[256]
-constexpr size_t kBandedSmem = sizeof(float2) * (2 * 4096 + kMaxClassScales * kBins + kBins) + sizeof(int) * kMaxClassScales;
+constexpr size_t kBandedSmem = sizeof(float2) * (2 * 4096 + kMaxClassScales * kBins + kBins) + sizeof(int) * kMaxClassScales + 16;
 
 template <int KIND, int LP>       // LP > 0: compile-time log2(P) (store offsets become immediates)
 __global__ void __launch_bounds__(256, 2)
@@ -673,9 +926,11 @@ fused_banded_kernel(const FusedParams prm) {
     float2* Zs = ex + 2 * 4096;
     float2* Estep = Zs + kMaxClassScales * kBins;
     int* s_ids = (int*)(Estep + kBins);
+    float* s_pow = (float*)(s_ids + kMaxClassScales);            // guard: two alternating output-energy counters
 
     const int tid = threadIdx.x;
     if (tid < prm.n_scales) s_ids[tid] = prm.scale_ids[tid];
+    if (tid < 2) s_pow[tid] = 0.f;
     const int r = tid & 15;            // column within the block of 16
     const int g = tid >> 4;            // m_lo in pass 1, n_lo in pass 2
 
@@ -696,6 +951,9 @@ fused_banded_kernel(const FusedParams prm) {
             raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
         }
         const float cm = chunk_mean<kChunkDec / 256>(raw, (float*)Zs);
+        if (prm.acc != nullptr && unit == 0)
+            chunk_energy_add<kChunkDec / 256>(raw, cm, (float*)Zs, prm.acc + c * prm.acc_stride + kGuardLevels + prm.class_idx,
+                                              prm.ech_weight);
 #pragma unroll
         for (int k = 0; k < kChunkDec / 256; ++k) ex[tid + 256 * k] = make_float2(raw[k] - cm, 0.f);
         __syncthreads();
@@ -733,6 +991,8 @@ fused_banded_kernel(const FusedParams prm) {
     const int64_t kstride = (int64_t)16 << lp;
     OutT* const out_c = (OutT*)prm.out + c * prm.c_stride + t0;
     int buf = 0;
+    int pend = -1;                                                       // guard: scale whose counter is flushed after the next barrier
+    float* const pow_c = prm.pow ? prm.pow + c * prm.pow_stride : nullptr;
     for (int it = 0; it < iters; ++it) {
         const int rel = col0 + it * 16 + r + (g << lp);                  // chunk-local sample of output k = 0
         const unsigned mask = valid_mask(rel, lp + 4, own_lo, own_hi);
@@ -747,15 +1007,28 @@ fused_banded_kernel(const FusedParams prm) {
 #pragma unroll
             for (int k = 1; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
             __syncthreads();
+            if (pend >= 0 && tid == 0) {                                  // every add for scale `pend` came before this barrier
+                atomicAdd(pow_c + s_ids[pend], s_pow[pend & 1] * (float)iters);
+                s_pow[pend & 1] = 0.f;
+            }
+            pend = -1;
             const float2* e2 = ex + buf * 4096 + g * 16 + r;
 #pragma unroll
             for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
             dft16<+1>(a);
             store_column<KIND>(out_c + (int64_t)s_ids[s] * prm.s_stride + rel, kstride, mask, a);
+            if (pow_c != nullptr && it == 0) {                            // sampled: the first column block of this unit
+                guard_pow_add<false>(a, mask, s_pow + (s & 1));
+                pend = s;
+            }
             buf ^= 1;
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) R[i] = cmul(R[i], Estep[g + 16 * i]);
+    }
+    if (pend >= 0) {
+        __syncthreads();
+        if (tid == 0) atomicAdd(pow_c + s_ids[pend], s_pow[pend & 1] * (float)iters);
     }
 }
 
@@ -768,7 +1041,7 @@ fused_banded_kernel(const FusedParams prm) {
 // smem: ex[4096] float2 | Zs[kMaxClassScales][256] float2 | Pc[2][kPcStride] float
 constexpr int kPcStride = kCoarse + 16;           // % 32 == 16: the two scales of a pair hit different banks
 constexpr int kPcFloats = 2 * kPcStride;
-constexpr size_t kInterpSmem = sizeof(float2) * (4096 + kMaxClassScales * kBins) + sizeof(float) * kPcFloats + sizeof(int) * kMaxClassScales;
+constexpr size_t kInterpSmem = sizeof(float2) * (4096 + kMaxClassScales * kBins) + sizeof(float) * kPcFloats + sizeof(int) * kMaxClassScales + 16;
 
 template <int KIND, int LU, int T>   // LU > 0: compile-time log2 of the coarse spacing (store offsets become immediates); T taps
 __device__ __forceinline__ void interp_rows(const float* __restrict__ pc, float* __restrict__ row,
@@ -900,12 +1173,14 @@ fused_interp_kernel(const FusedParams prm) {
     float2* Zs = ex + 4096;
     float* Pc = (float*)(Zs + kMaxClassScales * kBins);
     int* s_ids = (int*)(Pc + kPcFloats);
+    float* s_pow = (float*)(s_ids + kMaxClassScales);   // guard: output-energy counters of the two scales of a pass
     constexpr int NCOL = 8;                        // coarse columns per chunk
     constexpr int NSC = 16 / NCOL;                 // scales transformed per 16-lane pass
     constexpr int PCS = kPcStride;
 
     const int tid = threadIdx.x;
     if (tid < prm.n_scales) s_ids[tid] = prm.scale_ids[tid];
+    if (tid < 2) s_pow[tid] = 0.f;
     const int r = tid & 15;
     const int g = tid >> 4;
     const int col = r & (NCOL - 1);    // coarse column: chunk-local sample (NCOL n1 + col) * U
@@ -936,6 +1211,9 @@ fused_interp_kernel(const FusedParams prm) {
             raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
         }
         const float cm = chunk_mean<kChunkDec / 256>(raw, (float*)Zs);
+        if (prm.acc != nullptr && split == 0)
+            chunk_energy_add<kChunkDec / 256>(raw, cm, (float*)Zs, prm.acc + c * prm.acc_stride + kGuardLevels + prm.class_idx,
+                                              prm.ech_weight);
 #pragma unroll
         for (int k = 0; k < kChunkDec / 256; ++k) ex[tid + 256 * k] = make_float2(raw[k] - cm, 0.f);
         __syncthreads();
@@ -962,6 +1240,15 @@ fused_interp_kernel(const FusedParams prm) {
         for (int t = 0; t < kInterpT; ++t) c0[t] = 0.f;
     }
     float* const out_c = (float*)prm.out + c * prm.c_stride + t0;
+    // guard: coarse samples (g + 16 k) * NCOL + col of this thread that lie in the block's own range
+    unsigned own = 0;
+    if (prm.pow != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int iota = (g + 16 * k) * NCOL + col;
+            own |= (unsigned)(iota >= ia && iota < ib) << k;
+        }
+    }
     for (int pair = 0; pair < prm.n_scales; pair += NSC) {
         const int s = min(pair + sidx, prm.n_scales - 1);
         float2 a[16];
@@ -981,11 +1268,16 @@ fused_interp_kernel(const FusedParams prm) {
         float* pc = Pc + sidx * PCS + g * NCOL + col;             // iota = (g + 16 k) * NCOL + col
 #pragma unroll
         for (int k = 0; k < 16; ++k) pc[k * 16 * NCOL] = a[k].x * a[k].x + a[k].y * a[k].y;
+        if (prm.pow != nullptr) guard_pow_add<true>(a, own, s_pow + sidx);
         __syncthreads();
         // (3) polyphase interpolation + epilogue for the scales of this pass
         // (dealing the (scale, interval) pairs of a pass to the threads as one flat sequence, to save the
         // partial last round of 256 per scale, measured slower: whole idle warps cost nothing)
         const int nsc = min(NSC, prm.n_scales - pair);
+        if (prm.pow != nullptr && tid < NSC) {                     // the loop's closing barrier orders the reset
+            if (tid < nsc) atomicAdd(prm.pow + c * prm.pow_stride + s_ids[pair + tid], s_pow[tid] * (float)(1 << lu));
+            s_pow[tid] = 0.f;
+        }
         for (int sl = 0; sl < nsc; ++sl) {
             const float* pcs = Pc + sl * PCS;
             float* row = out_c + (int64_t)s_ids[pair + sl] * prm.s_stride;
@@ -1022,7 +1314,7 @@ fused_interp_kernel(const FusedParams prm) {
 // of the wide classes brings it to the full rate.
 // smem: B0[4096] (FFT ping, then exchange) | B1[256 x 17] (FFT pong, then alias tile / coarse rows) | ids
 constexpr int kTileA = 256 * 17;   // alias tile: 16 columns per bin, rows padded to 17 (conflict-free, constant offsets)
-constexpr size_t kWide2Smem = sizeof(float2) * (4096 + kTileA) + sizeof(int) * kMaxClassScales;
+constexpr size_t kWide2Smem = sizeof(float2) * (4096 + kTileA) + sizeof(int) * kMaxClassScales + 16;
 
 // Bins 0 .. 511 of the 2048-point forward FFT of the real chunk in `a` (2048 float2, imaginary parts
 // zero): five radix-4 Stockham passes (two butterflies per thread), then the last radix-2 pass only
@@ -1064,8 +1356,10 @@ fused_wide2_kernel(const FusedParams prm) {
     float2* B0 = (float2*)smem_raw;
     float2* B1 = B0 + 4096;
     int* s_ids = (int*)(B1 + kTileA);
+    float* s_pow = (float*)(s_ids + kMaxClassScales);
 
     const int tid = threadIdx.x;
+    if (tid < 2) s_pow[tid] = 0.f;
     const int r = tid & 15;
     const int g = tid >> 4;
     const int64_t q = blockIdx.x % prm.n_chunks;
@@ -1089,6 +1383,9 @@ fused_wide2_kernel(const FusedParams prm) {
             raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
         }
         const float cm = chunk_mean<NV>(raw, (float*)(B1 + 3072));
+        if (prm.acc != nullptr)
+            chunk_energy_add<NV>(raw, cm, (float*)(B1 + 3072), prm.acc + c * prm.acc_stride + kGuardLevels + prm.class_idx,
+                                 prm.ech_weight);
 #pragma unroll
         for (int k = 0; k < NV; ++k) B0[tid + 256 * k] = make_float2(raw[k] - cm, 0.f);
         __syncthreads();
@@ -1105,6 +1402,14 @@ fused_wide2_kernel(const FusedParams prm) {
     float2* const ex = B0;
     float* const Pc = (float*)B1;
     const int col = r & 7, sidx = r >> 3;
+    unsigned own = 0;                                              // guard: owned coarse samples (g + 16 k) * 8 + col
+    if (prm.pow != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int iota = (g + 16 * k) * 8 + col;
+            own |= (unsigned)(iota >= ia && iota < ib) << k;
+        }
+    }
     __syncthreads();                                               // the spectrum is in registers: both buffers are free
     for (int pair = 0; pair < prm.n_scales; pair += 2) {
         // the two alias blocks (bins m' and m' + 256) folded onto the 8 columns, both scales of the pass
@@ -1142,7 +1447,13 @@ fused_wide2_kernel(const FusedParams prm) {
         float* pc = Pc + sidx * kPcStride + g * 8 + col;           // coarse index (g + 16 k) * 8 + col
 #pragma unroll
         for (int k = 0; k < 16; ++k) pc[k * 128] = a[k].x * a[k].x + a[k].y * a[k].y;
+        if (prm.pow != nullptr) guard_pow_add<true>(a, own, s_pow + sidx);
         __syncthreads();
+        if (prm.pow != nullptr && tid < 2) {                        // the loop's closing barrier orders the reset
+            if (pair + tid < prm.n_scales)
+                atomicAdd(prm.pow + c * prm.pow_stride + s_ids[pair + tid], s_pow[tid] * (float)(1 << lu));
+            s_pow[tid] = 0.f;
+        }
         for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl) {
             const float* pcs = Pc + sl * kPcStride;
             float* row = out_c + (int64_t)s_ids[pair + sl] * prm.s_stride;
@@ -1155,7 +1466,7 @@ fused_wide2_kernel(const FusedParams prm) {
 
 // ---------------------------------------------------------------------------- full spectrum
 // smem: Yf[4096] | ex[4096] | A[256 x 17] | ids[64] | nmu[64]
-constexpr size_t kFullSmem = sizeof(float2) * (2 * 4096 + kTileA) + sizeof(int) * 2 * kMaxFullScales;
+constexpr size_t kFullSmem = sizeof(float2) * (2 * 4096 + kTileA) + sizeof(int) * 2 * kMaxFullScales + 16;
 
 // radix-16 over the aliases m' + 256 mu of spectrum bin m' = tid, pruned to the first NMU
 // aliases (the others are empty for a filter that occupies only NMU blocks of 256 bins)
@@ -1182,8 +1493,10 @@ fused_full_kernel(const FusedParams prm) {
     float2* A = ex + kFullN;
     int* s_ids = (int*)(A + kTileA);
     int* s_nmu = s_ids + kMaxFullScales;
+    float* s_pow = (float*)(s_nmu + kMaxFullScales);             // guard: two alternating output-energy counters
 
     const int tid = threadIdx.x;
+    if (tid < 2) s_pow[tid] = 0.f;
     const int r = tid & 15;
     const int g = tid >> 4;
     const int64_t q = blockIdx.x % prm.n_chunks;
@@ -1207,6 +1520,9 @@ fused_full_kernel(const FusedParams prm) {
         for (int k = 0; k < kFullN / 256; ++k)                    // zero padding outside the readable range
             val[k] = (inside >> k & 1) ? (float)((double)raw[k] - mu) : 0.f;
         const float cm = chunk_mean<kFullN / 256>(val, (float*)ex + 2048);   // (behind the forward FFT's spill into ex)
+        if (prm.acc != nullptr)
+            chunk_energy_add<kFullN / 256>(val, cm, (float*)ex + 2048, prm.acc + c * prm.acc_stride + kGuardLevels + prm.class_idx,
+                                           prm.ech_weight);
 #pragma unroll
         for (int k = 0; k < kFullN / 256; ++k) A[tid + 256 * k] = make_float2(val[k] - cm, 0.f);
         __syncthreads();
@@ -1223,6 +1539,8 @@ fused_full_kernel(const FusedParams prm) {
     const unsigned mask = valid_mask(rel, 8, (int)prm.offset, (int)min(prm.offset + prm.hop, prm.n - t0));
     OutT* const out_c = (OutT*)prm.out + c * prm.c_stride + t0;
     if (tid < prm.n_scales) { s_ids[tid] = prm.scale_ids[tid]; s_nmu[tid] = prm.scale_nmu[tid]; }
+    // guard: the output energy of every scale is measured on every fourth chunk (block-uniform)
+    float* const pow_c = (prm.pow != nullptr && (q & 3) == 0) ? prm.pow + c * prm.pow_stride : nullptr;
     __syncthreads();
     for (int s = 0; s < prm.n_scales; ++s) {
         float2 a[16];
@@ -1237,6 +1555,10 @@ fused_full_kernel(const FusedParams prm) {
         else if (nmu == 8) full_prepass<8>(Yf, tab, A, tw4k);
         else full_prepass<16>(Yf, tab, A, tw4k);
         __syncthreads();
+        if (pow_c != nullptr && s > 0 && tid == 0) {                 // every add for scale s - 1 came before this barrier
+            atomicAdd(pow_c + s_ids[s - 1], s_pow[(s - 1) & 1] * prm.pow_weight);
+            s_pow[(s - 1) & 1] = 0.f;
+        }
         // pass 1 of the 256-point transforms (16 columns)
 #pragma unroll
         for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 17 + r];
@@ -1251,9 +1573,15 @@ fused_full_kernel(const FusedParams prm) {
         for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
         dft16<+1>(a);
         store_column<KIND>(out_c + (int64_t)s_ids[s] * prm.s_stride + rel, 256, mask, a);
+        if (pow_c != nullptr) guard_pow_add<false>(a, mask, s_pow + (s & 1));
         // no trailing barrier: the next scale's pre-pass writes A, whose readers all passed
         // the second barrier above; its pass 1 writes ex only after the next first barrier,
         // which every thread reaches after finishing the reads of ex just done.
+    }
+    if (pow_c != nullptr) {
+        __syncthreads();
+        const int s = prm.n_scales - 1;
+        if (tid == 0) atomicAdd(pow_c + s_ids[s], s_pow[s & 1] * prm.pow_weight);
     }
 }
 
@@ -1308,8 +1636,28 @@ template <typename TIn>
 static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels, int64_t n,
                     int64_t x_stride, int64_t halo_l, int64_t halo_r, const double* d_means,
                     void* out, int64_t s_stride, int64_t c_stride, cudaStream_t st) {
+    // ---- accuracy guard: per-execute accumulators ------------------------------------
+    const bool guard = p->guard;
+    const int acc_stride = kGuardLevels + (int)p->classes.size();
+    if (guard) {
+        if (p->guard_cap < n_channels) {               // (the previous execute has completed: it waited for its verdict)
+            if (p->d_guard_acc) cudaFree(p->d_guard_acc);
+            if (p->d_guard_pow) cudaFree(p->d_guard_pow);
+            if (p->d_guard_flags) cudaFree(p->d_guard_flags);
+            if (p->h_guard_flags) cudaFreeHost(p->h_guard_flags);
+            p->d_guard_acc = nullptr; p->d_guard_pow = nullptr; p->d_guard_flags = p->h_guard_flags = nullptr; p->guard_cap = 0;
+            GCWT_CUDA_OK(cudaMalloc((void**)&p->d_guard_acc, sizeof(double) * acc_stride * n_channels));
+            GCWT_CUDA_OK(cudaMalloc((void**)&p->d_guard_pow, sizeof(float) * p->n_scales * n_channels));
+            GCWT_CUDA_OK(cudaMalloc((void**)&p->d_guard_flags, (size_t)p->n_scales * n_channels));
+            GCWT_CUDA_OK(cudaMallocHost((void**)&p->h_guard_flags, (size_t)p->n_scales * n_channels));
+            p->guard_cap = n_channels;
+        }
+        GCWT_CUDA_OK(cudaMemsetAsync(p->d_guard_acc, 0, sizeof(double) * acc_stride * n_channels, st));
+        GCWT_CUDA_OK(cudaMemsetAsync(p->d_guard_pow, 0, sizeof(float) * p->n_scales * n_channels, st));
+    }
     // ---- pyramid geometry ---------------------------------------------------------
-    const int levels = std::max(p->max_level, 0);
+    // (the guard needs band energies two octaves below the deepest level in use: two more, tiny, levels)
+    const int levels = std::max(p->max_level, 0) + ((guard && p->max_level > 0) ? 2 : 0);
     std::vector<LevelGeom> lv(levels + 1);
     lv[0].lo = -halo_l; lv[0].hi = n + halo_r;                    // [lo, hi)
     size_t total = 0;
@@ -1329,13 +1677,16 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
     const int sp_pyr = prof_begin(p, 0, st);
     for (int j = 1; j <= levels; ++j) {
         dim3 grid((unsigned)((lv[j].len + kPyrTile - 1) / kPyrTile), (unsigned)n_channels);
+        double* acc = guard ? p->d_guard_acc : nullptr;
+        const int64_t seg_in = (n + (int64_t(1) << (j - 1)) - 1) >> (j - 1), seg_out = (n + (int64_t(1) << j) - 1) >> j;
         if (j == 1)
             pyramid_kernel<TIn, true><<<grid, 256, 0, st>>>(x, x_stride, lv[0].lo, lv[0].hi, d_means, lv[1].ptr,
-                                                            lv[1].stride, lv[1].lo, lv[1].len);
+                                                            lv[1].stride, lv[1].lo, lv[1].len, acc, acc_stride, j,
+                                                            seg_in, seg_out);
         else
             pyramid_kernel<float, false><<<grid, 256, 0, st>>>(lv[j - 1].ptr, lv[j - 1].stride, lv[j - 1].lo,
                                                                lv[j - 1].hi, nullptr, lv[j].ptr, lv[j].stride,
-                                                               lv[j].lo, lv[j].len);
+                                                               lv[j].lo, lv[j].len, acc, acc_stride, j, seg_in, seg_out);
         count_launch();
     }
     prof_end(p, sp_pyr, st);
@@ -1363,6 +1714,12 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prm.out = out; prm.s_stride = s_stride; prm.c_stride = c_stride;
         prm.inv_nc = 1.0f / (float)fc.nc_full;
         prm.log2u = fc.log2u; prm.coef = fc.d_coef; prm.twf = p->d_twiddle; prm.scale_nmu = fc.d_scale_nmu;
+        prm.acc = guard ? p->d_guard_acc : nullptr; prm.acc_stride = acc_stride;
+        prm.class_idx = (int)(&fc - p->classes.data());
+        prm.pow = guard ? p->d_guard_pow : nullptr; prm.pow_stride = p->n_scales;
+        prm.pow_weight = 1.f;
+        // chunk energy -> energy of the segment at the full rate: D samples per decimated one, chunks overlap
+        prm.ech_weight = (float)((double)(fc.level >= 0 ? (int64_t(1) << fc.level) : 1) * (double)fc.hop / (double)fc.nc_full);
         if (fc.level >= 0 && fc.interp && fc.wide && fc.d_table2) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1370,6 +1727,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.offset = fc.offset2; prm.hop = fc.hop2;
             prm.n_chunks = (n + fc.hop2 - 1) / fc.hop2;
             prm.table = fc.d_table2;
+            prm.ech_weight = (float)((double)(int64_t(1) << fc.level) * (double)fc.hop2 / (double)(2 * fc.nc_full));
             prm.p_cols = 8; prm.log2p = 3; prm.units_per_chunk = 1;
             prm.iters = rows_aligned ? 1 : 0;                      // 128-bit stores allowed
             const int64_t nblk = n_channels * prm.n_chunks;
@@ -1416,6 +1774,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.log2d = 0; prm.p_cols = 16; prm.log2p = 4; prm.iters = 1; prm.units_per_chunk = 1;
             const int64_t nblk = n_channels * prm.n_chunks;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
+            prm.pow_weight = (float)((double)prm.n_chunks / (double)((prm.n_chunks + 3) / 4));   // every fourth chunk is measured
             launch_full<TIn>(p->out_kind, (unsigned)nblk, cs, prm);
         }
         count_launch();
@@ -1466,6 +1825,87 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prof_end(p, sp, st);
     }
     GCWT_CUDA_OK(cudaGetLastError());
+    return GCWT_OK;
+}
+
+// ---- accuracy guard: verdict per (channel, scale) -----------------------------------------------
+__global__ void guard_eval_kernel(int n_scales, const ScaleInfo* __restrict__ scales, const float* __restrict__ gain,
+                                  const float* __restrict__ q, const int32_t* __restrict__ cls,
+                                  const double* __restrict__ acc, int acc_stride, const float* __restrict__ pow,
+                                  double tol2, unsigned char* __restrict__ flags) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (s >= n_scales) return;
+    unsigned char flag = 0;
+    const int ci = cls[s];
+    if (ci >= 0) {
+        const double* a = acc + (int64_t)c * acc_stride;
+        const int lev = scales[s].level;
+        const double eps = 5.9604644775390625e-08;                // 2^-24
+        const double qs = (double)q[s];
+        // rounding of the chunk transform against the (mean-removed) energy of the chunks
+        double bound = (kGuardKRound * eps) * (kGuardKRound * eps) * qs * a[kGuardLevels + ci];
+        if (lev >= 0) {
+            // a[j] is the plain sum of squares of level j: its energy at the full rate is 2^j times that
+            const float* gs = gain + (int64_t)s * kGuardSlots;
+            for (int b = 0; b <= lev; ++b) {
+                const double e_lo = b + 2 < kGuardLevels ? ldexp(a[b + 2], b + 2) : 0.0;
+                const double eb = fmax(ldexp(a[b], b) - e_lo, 0.0);  // octave b (two octaves wide: the transition bands smear)
+                bound += (double)gs[b] * eb;
+            }
+            if (lev + 1 < kGuardLevels) bound += (double)gs[lev + 1] * ldexp(a[lev + 1], lev + 1);
+            double stage = 0.0;                                    // storage rounding of the pyramid's stages
+            for (int j = 1; j <= lev; ++j) stage += ldexp(a[j], j + j - lev);
+            bound += (kGuardKStage * eps) * (kGuardKStage * eps) * qs * stage / 3.0;
+        }
+        flag = bound > tol2 * (double)pow[(int64_t)c * n_scales + s];
+    }
+    flags[(int64_t)c * n_scales + s] = flag;
+}
+
+int guard_resolve(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, int64_t n_samples,
+                  int64_t x_stride, int64_t halo_l, int64_t halo_r, const double* d_means,
+                  void* out, int64_t s_stride, int64_t c_stride, cudaStream_t st) {
+    if (!p->guard) return GCWT_OK;
+    const int S = p->n_scales;
+    const int acc_stride = kGuardLevels + (int)p->classes.size();
+    guard_eval_kernel<<<dim3((S + 127) / 128, (unsigned)n_channels), 128, 0, st>>>(
+        S, p->d_scales, p->d_guard_gain, p->d_guard_q, p->d_guard_class, p->d_guard_acc, acc_stride, p->d_guard_pow,
+        p->guard_tol * p->guard_tol, p->d_guard_flags);
+    count_launch();
+    GCWT_CUDA_OK(cudaMemcpyAsync(p->h_guard_flags, p->d_guard_flags, (size_t)S * n_channels, cudaMemcpyDeviceToHost, st));
+    GCWT_CUDA_OK(cudaEventRecord(p->ev_guard, st));
+    GCWT_CUDA_OK(cudaEventSynchronize(p->ev_guard));
+    p->guard_last = 0;
+    p->guard_checked += (int64_t)S * n_channels;
+    std::fill(p->guard_last_flags.begin(), p->guard_last_flags.end(), 0);
+    const size_t in_el = in_type == GCWT_F32 ? 4 : 8;
+    const size_t out_el = p->out_kind == GCWT_OUT_COMPLEX ? 8 : 4;
+    if (getenv("GCWT_GUARD_DUMP")) {                               // developer aid: the measured energies of channel 0
+        std::vector<double> a(acc_stride);
+        std::vector<float> pw(S);
+        cudaMemcpy(a.data(), p->d_guard_acc, sizeof(double) * acc_stride, cudaMemcpyDeviceToHost);
+        cudaMemcpy(pw.data(), p->d_guard_pow, sizeof(float) * S, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "gcwt guard e_j:");
+        for (int j = 0; j < kGuardLevels; ++j) fprintf(stderr, " %.3e", std::ldexp(a[j], j));
+        fprintf(stderr, "\ngcwt guard chunk energies:");
+        for (int j = kGuardLevels; j < acc_stride; ++j) fprintf(stderr, " %.3e", a[j]);
+        fprintf(stderr, "\ngcwt guard pow:");
+        for (int s2 = 0; s2 < S; ++s2) fprintf(stderr, " %.3e", pw[s2]);
+        fprintf(stderr, "\n");
+    }
+    for (int64_t c = 0; c < n_channels; ++c) {
+        std::vector<int> ids;
+        for (int s2 = 0; s2 < S; ++s2)
+            if (p->h_guard_flags[c * S + s2]) { ids.push_back(s2); p->guard_last_flags[s2] = 1; }
+        if (ids.empty()) continue;
+        p->guard_last += (int64_t)ids.size();
+        const int sp = prof_begin(p, 3, st);
+        int rc = generic_execute(p, ids, (const char*)x + in_el * c * x_stride, in_type, 1, n_samples, x_stride, halo_l, halo_r,
+                                 d_means + c, (char*)out + out_el * c * c_stride, s_stride, c_stride, st, true);
+        prof_end(p, sp, st);
+        if (rc) return rc;
+    }
+    p->guard_total += p->guard_last;
     return GCWT_OK;
 }
 

@@ -133,7 +133,7 @@ __global__ void generic_multiply_kernel(const typename cplx_of<T>::type* __restr
 }
 
 // ----------------------------------------------------------------------------- epilogue
-template <typename T, int KIND>
+template <typename T, typename TOut, int KIND>
 __global__ void generic_epilogue_kernel(const typename cplx_of<T>::type* __restrict__ Z, int nfft,
                                         int64_t item0, int64_t n_chunks, int64_t hop, int64_t offset,
                                         int64_t n, const int* __restrict__ ids, int sb, void* out,
@@ -148,13 +148,14 @@ __global__ void generic_epilogue_kernel(const typename cplx_of<T>::type* __restr
     if (t >= n) return;
     const C v = Z[((int64_t)ib * sb + s) * nfft + offset + i];
     const int64_t o = c * c_stride + (int64_t)ids[s] * s_stride + t;
-    if (KIND == GCWT_OUT_COMPLEX) ((C*)out)[o] = v;
-    else if (KIND == GCWT_OUT_AMPLITUDE) ((T*)out)[o] = sqrt(v.x * v.x + v.y * v.y);
-    else ((T*)out)[o] = v.x * v.x + v.y * v.y;
+    typedef typename cplx_of<TOut>::type CO;
+    if (KIND == GCWT_OUT_COMPLEX) ((CO*)out)[o] = mk<TOut>((TOut)v.x, (TOut)v.y);
+    else if (KIND == GCWT_OUT_AMPLITUDE) ((TOut*)out)[o] = (TOut)sqrt(v.x * v.x + v.y * v.y);
+    else ((TOut*)out)[o] = (TOut)(v.x * v.x + v.y * v.y);
 }
 
 // ----------------------------------------------------------------------------- driver
-template <typename TIn, typename T>
+template <typename TIn, typename T, typename TOut>
 static int generic_run(gcwt_plan* p, const std::vector<int>& ids, const TIn* x, int64_t n_channels,
                        int64_t n, int64_t x_stride, int64_t halo_l, int64_t halo_r,
                        const double* d_means, void* out, int64_t s_stride, int64_t c_stride,
@@ -213,15 +214,15 @@ static int generic_run(gcwt_plan* p, const std::vector<int>& ids, const TIn* x, 
             dim3 ge((unsigned)((hop + tpb - 1) / tpb), sbn, ibn);
             switch (p->out_kind) {
                 case GCWT_OUT_COMPLEX:
-                    generic_epilogue_kernel<T, GCWT_OUT_COMPLEX><<<ge, tpb, 0, st>>>(
+                    generic_epilogue_kernel<T, TOut, GCWT_OUT_COMPLEX><<<ge, tpb, 0, st>>>(
                         za, (int)nfft, i0, n_chunks, hop, offset, n, d_ids + s0, sbn, out, s_stride, c_stride);
                     break;
                 case GCWT_OUT_AMPLITUDE:
-                    generic_epilogue_kernel<T, GCWT_OUT_AMPLITUDE><<<ge, tpb, 0, st>>>(
+                    generic_epilogue_kernel<T, TOut, GCWT_OUT_AMPLITUDE><<<ge, tpb, 0, st>>>(
                         za, (int)nfft, i0, n_chunks, hop, offset, n, d_ids + s0, sbn, out, s_stride, c_stride);
                     break;
                 default:
-                    generic_epilogue_kernel<T, GCWT_OUT_POWER><<<ge, tpb, 0, st>>>(
+                    generic_epilogue_kernel<T, TOut, GCWT_OUT_POWER><<<ge, tpb, 0, st>>>(
                         za, (int)nfft, i0, n_chunks, hop, offset, n, d_ids + s0, sbn, out, s_stride, c_stride);
                     break;
             }
@@ -235,20 +236,27 @@ static int generic_run(gcwt_plan* p, const std::vector<int>& ids, const TIn* x, 
 int generic_execute(gcwt_plan* p, const std::vector<int>& ids, const void* x, int in_type,
                     int64_t n_channels, int64_t n_samples, int64_t x_stride, int64_t halo_l,
                     int64_t halo_r, const double* d_means, void* out, int64_t s_stride,
-                    int64_t c_stride, cudaStream_t st) {
+                    int64_t c_stride, cudaStream_t st, bool fp64_for_fp32_plan) {
     if (ids.empty()) return GCWT_OK;
     if (p->compute_type == GCWT_F64) {
         if (in_type == GCWT_F32)
-            return generic_run<float, double>(p, ids, (const float*)x, n_channels, n_samples, x_stride, halo_l,
-                                              halo_r, d_means, out, s_stride, c_stride, st);
-        return generic_run<double, double>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
-                                           halo_r, d_means, out, s_stride, c_stride, st);
+            return generic_run<float, double, double>(p, ids, (const float*)x, n_channels, n_samples, x_stride, halo_l,
+                                                      halo_r, d_means, out, s_stride, c_stride, st);
+        return generic_run<double, double, double>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
+                                                   halo_r, d_means, out, s_stride, c_stride, st);
+    }
+    if (fp64_for_fp32_plan) {              // accuracy guard: fp64 arithmetic, the plan's fp32 output
+        if (in_type == GCWT_F32)
+            return generic_run<float, double, float>(p, ids, (const float*)x, n_channels, n_samples, x_stride, halo_l,
+                                                     halo_r, d_means, out, s_stride, c_stride, st);
+        return generic_run<double, double, float>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
+                                                  halo_r, d_means, out, s_stride, c_stride, st);
     }
     if (in_type == GCWT_F32)
-        return generic_run<float, float>(p, ids, (const float*)x, n_channels, n_samples, x_stride, halo_l,
-                                         halo_r, d_means, out, s_stride, c_stride, st);
-    return generic_run<double, float>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
-                                      halo_r, d_means, out, s_stride, c_stride, st);
+        return generic_run<float, float, float>(p, ids, (const float*)x, n_channels, n_samples, x_stride, halo_l,
+                                                halo_r, d_means, out, s_stride, c_stride, st);
+    return generic_run<double, float, float>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
+                                             halo_r, d_means, out, s_stride, c_stride, st);
 }
 
 // ----------------------------------------------------------------------------- probe

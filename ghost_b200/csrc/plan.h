@@ -67,6 +67,17 @@ struct FastClass {
     float* d_coef = nullptr;
 };
 
+// ---- execute-time accuracy guard (fp32 plans) -------------------------------------------------
+// The band-limited classes drop each filter's response outside the kept band (band_tol) and rely on a
+// decimator with a finite stop band, and every fp32 class rounds against the energy of the chunk it
+// transforms; all three are harmless unless the recording holds far more energy outside a scale's band
+// than inside it.  Per (channel, scale) the guard compares a bound on that error, built from measured
+// octave-band energies, with the measured output energy, and re-computes the pairs that fail in fp64.
+constexpr int kGuardSlots = 18;     // octave slots b = 0 .. level + 1 of the per-scale error gains
+constexpr int kGuardLevels = 20;    // pyramid energies e_0 .. e_(max_level + 2)
+constexpr double kGuardKRound = 6.0;   // chunk-transform rounding: err^2 <= (k eps)^2 q E_chunk   (measured 1 .. 4.7)
+constexpr double kGuardKStage = 2.0;   // pyramid storage rounding: err^2 <= (k eps)^2 q sum_j E_j 2^(j-l) / 3 (measured ~1)
+
 struct Workspace {
     void* ptr = nullptr;
     size_t bytes = 0;
@@ -104,6 +115,20 @@ struct gcwt_plan {
     cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {nullptr, nullptr, nullptr};
     double* d_partial = nullptr;            // scratch of the mean reduction
     int64_t partial_cap = 0;
+    // accuracy guard: plan-time tables (per scale) and per-execute accumulators (per channel)
+    bool guard = false;
+    double guard_tol = 5e-6;
+    float* d_guard_gain = nullptr;          // [n_scales][kGuardSlots] squared error gain per octave slot
+    float* d_guard_q = nullptr;             // [n_scales] mean |H|^2 over the chunk grid
+    int32_t* d_guard_class = nullptr;       // [n_scales] index into classes (-1: not guarded)
+    double* d_guard_acc = nullptr;          // [channels][kGuardLevels + n_classes] band and chunk energies
+    float* d_guard_pow = nullptr;           // [channels][n_scales] measured output energy
+    unsigned char* d_guard_flags = nullptr; // [channels][n_scales]
+    unsigned char* h_guard_flags = nullptr; // pinned copy
+    int64_t guard_cap = 0;                  // channels the accumulators are sized for
+    cudaEvent_t ev_guard = nullptr;
+    int64_t guard_last = 0, guard_total = 0, guard_checked = 0;   // re-computed (channel, scale) pairs
+    std::vector<unsigned char> guard_last_flags;                  // any-channel flag per scale of the last call
 };
 
 namespace gcwt {
@@ -118,7 +143,11 @@ void prof_end(gcwt_plan* p, int idx, cudaStream_t st);
 int generic_execute(gcwt_plan* p, const std::vector<int>& ids, const void* x, int in_type,
                     int64_t n_channels, int64_t n_samples, int64_t x_stride,
                     int64_t halo_l, int64_t halo_r, const double* d_means,
-                    void* out, int64_t s_stride, int64_t c_stride, cudaStream_t st);
+                    void* out, int64_t s_stride, int64_t c_stride, cudaStream_t st,
+                    bool fp64_for_fp32_plan = false);
+int guard_resolve(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, int64_t n_samples,
+                  int64_t x_stride, int64_t halo_l, int64_t halo_r, const double* d_means,
+                  void* out, int64_t s_stride, int64_t c_stride, cudaStream_t st);
 int fast_execute(gcwt_plan* p, const void* x, int in_type,
                  int64_t n_channels, int64_t n_samples, int64_t x_stride,
                  int64_t halo_l, int64_t halo_r, const double* d_means,

@@ -38,7 +38,7 @@ class CwtPlan:
     """Device tables for one set of scales."""
 
     def __init__(self, lengths, k_first, n_terms, terms, *, dtype=np.float32, output="amplitude",
-                 device=0, force_generic=False, no_interp=False, band_tol=0.0):
+                 device=0, force_generic=False, no_interp=False, band_tol=0.0, guard=True, guard_tol=0.0):
         dtype = np.dtype(dtype)
         if dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
             raise ValueError("dtype must be float32 or float64 but got {}".format(dtype))
@@ -62,8 +62,10 @@ class CwtPlan:
         desc.compute_type = _lib.F32 if dtype == np.float32 else _lib.F64
         desc.out_kind = OUT_KINDS[output]
         desc.device = self.device
-        desc.flags = (_lib.FLAG_FORCE_GENERIC if force_generic else 0) | (_lib.FLAG_NO_INTERP if no_interp else 0)
+        desc.flags = (_lib.FLAG_FORCE_GENERIC if force_generic else 0) | (_lib.FLAG_NO_INTERP if no_interp else 0) \
+            | (0 if guard else _lib.FLAG_NO_GUARD)
         desc.band_tol = float(band_tol)
+        desc.guard_tol = float(guard_tol)
         handle = C.c_void_p()
         _lib.check(self.lib.gcwt_plan_create(C.byref(handle), C.byref(desc)))
         self._h = handle
@@ -77,6 +79,17 @@ class CwtPlan:
         out = np.empty(self.n_scales, dtype=np.int32)
         _lib.check(self.lib.gcwt_plan_levels(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
+
+    def guard_stats(self):
+        """Accuracy guard of the fp32 paths (include/ghost_cwt.h, gcwt_guard_stats): dict with the
+        (channel, scale) pairs re-computed in fp64 by the last execute, in total, the pairs examined
+        so far, and a per-scale flag array of the last execute."""
+        last, total, checked = C.c_int64(), C.c_int64(), C.c_int64()
+        flags = np.zeros(self.n_scales, dtype=np.uint8)
+        _lib.check(self.lib.gcwt_guard_stats(self._h, C.byref(last), C.byref(total), C.byref(checked),
+                                             flags.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        return {"last": int(last.value), "total": int(total.value), "checked": int(checked.value),
+                "scales": flags.astype(bool)}
 
     def workspace_bytes(self):
         return int(self.lib.gcwt_plan_workspace_bytes(self._h))

@@ -55,11 +55,19 @@ class ContinuousWaveletTransform(WaveletTransform):
         What the device epilogue writes.  Default 'amplitude' (what the reference stores).
     device : int, optional
         CUDA device ordinal.  Default 0.
+    band_tol : float, optional
+        float32 only: out-of-band filter energy (amplitude ratio) the band-limited kernels may drop.
+        Default 3e-7.
+    guard : bool, optional
+        float32 only: measure, per call, whether the recording's spectrum lets the float32 kernels hold
+        the 1e-5 bar for every (channel, scale) and re-compute the ones that cannot in float64
+        (``guard_tol``: the bound that triggers it, default 5e-6).  Default True.
     """
 
     _PLAN_CACHE_SIZE = 4
 
-    def __init__(self, *, wavelet=None, dtype=None, output=None, device=None):
+    def __init__(self, *, wavelet=None, dtype=None, output=None, device=None, band_tol=None, guard=None,
+                 guard_tol=None):
         if wavelet is None:
             wavelet = morse.Morse()
         self._wavelet = wavelet
@@ -70,6 +78,11 @@ class ContinuousWaveletTransform(WaveletTransform):
             raise ValueError("'output' must be 'amplitude', 'power' or 'complex' but got {}".format(output))
         self._output = output
         self._device = 0 if device is None else int(device)
+        self._band_tol = 0.0 if band_tol is None else float(band_tol)
+        if self._band_tol < 0:
+            raise ValueError("'band_tol' must be positive")
+        self._guard = True if guard is None else bool(guard)
+        self._guard_tol = 0.0 if guard_tol is None else float(guard_tol)
 
         self._frequencies = None
         self._fs = None
@@ -108,12 +121,13 @@ class ContinuousWaveletTransform(WaveletTransform):
         omegas = self._hz_to_norm_radians(frequencies)
         lengths = self.wavelet.compute_lengths(omegas)
         key = (float(self.wavelet.gamma), float(self.wavelet.beta), float(self._fs), self._dtype.str,
-               self._output, self._device, frequencies.tobytes())
+               self._output, self._device, self._band_tol, self._guard, self._guard_tol, frequencies.tobytes())
         plan = self._plans.get(key)
         if plan is None:
             k_first, n_terms, terms = scale_tables(self.wavelet, omegas, lengths)
             plan = CwtPlan(lengths, k_first, n_terms, terms, dtype=self._dtype, output=self._output,
-                           device=self._device)
+                           device=self._device, band_tol=self._band_tol, guard=self._guard,
+                           guard_tol=self._guard_tol)
             if len(self._plans) >= self._PLAN_CACHE_SIZE:
                 old = next(iter(self._plans))
                 self._plans.pop(old).close()

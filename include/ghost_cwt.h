@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GCWT_VERSION 100
+#define GCWT_VERSION 200
 
 /* error codes */
 #define GCWT_OK            0
@@ -56,6 +56,8 @@ extern "C" {
 #define GCWT_FLAG_NO_INTERP     2   /* fp32 amplitude/power: compute every output sample with the pruned
                                        inverse FFT instead of coarse grid + polyphase interpolation */
 
+#define GCWT_FLAG_NO_GUARD      4   /* fp32 only: skip the execute-time accuracy guard (see gcwt_guard_stats) */
+
 typedef struct gcwt_plan gcwt_plan;
 
 typedef struct gcwt_plan_desc {
@@ -70,6 +72,8 @@ typedef struct gcwt_plan_desc {
     int32_t        flags;        /* GCWT_FLAG_*                                                   */
     double         band_tol;     /* fp32 fast path: allowed out-of-band filter energy (amplitude
                                     ratio); 0 selects the default 3e-7                            */
+    double         guard_tol;    /* fp32 accuracy guard: largest tolerated bound on a scale's relative
+                                    L2 error before it is re-computed in fp64; 0 selects 5e-6      */
 } gcwt_plan_desc;
 
 /* Build device tables for a set of scales.  Replaces the per-scale kernel synthesis
@@ -158,6 +162,23 @@ int gcwt_analytic_signal(const double *x, int64_t n, double *out_complex, int32_
  * over the whole (S, N) array (ghost/wave/transforms.py:360-366).  out_host[0] = mean, [1] = std. */
 int gcwt_moments(const void *x_dev, int32_t type, int64_t n, int32_t square, double *out_host,
                  int32_t device, void *stream);
+
+/* Execute-time accuracy guard of the fp32 paths.  The reference convolves with an exact L-tap FIR for
+ * any input spectrum (ghost/sigtools/convolution.py:72-87).  The fp32 fused kernels are exact only up
+ * to (a) the filter response dropped outside the band they keep (band_tol), (b) the stop band of the
+ * decimation pyramid and (c) fp32 rounding against the energy of the chunk being transformed.  All
+ * three are far below the 1e-5 bar unless a scale's true output is orders of magnitude weaker than
+ * what the recording holds elsewhere in the spectrum (blue or high-passed recordings, a weak tone
+ * beside a strong one).  During gcwt_execute the kernels therefore measure octave-band energies of
+ * every channel and the output energy of every (channel, scale); a bound on the three errors is
+ * compared with guard_tol, and the pairs that fail are re-computed with the fp64 generic path (cast
+ * to the plan's fp32 output).  gcwt_execute waits for the verdict, i.e. it synchronises `stream`
+ * once per call unless the plan was created with GCWT_FLAG_NO_GUARD.
+ *   last_pairs   (channel, scale) pairs re-computed by the last gcwt_execute
+ *   total_pairs  same, accumulated since plan creation;  checked_pairs: pairs examined so far
+ *   scale_flags  optional [n_scales] bytes: 1 where the last call re-computed that scale for any channel */
+int gcwt_guard_stats(const gcwt_plan *plan, int64_t *last_pairs, int64_t *total_pairs,
+                     int64_t *checked_pairs, unsigned char *scale_flags);
 
 /* Bytes of device workspace the plan currently holds (grows on demand in execute). */
 size_t gcwt_plan_workspace_bytes(const gcwt_plan *plan);

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_lib.EXPORTS) == names
-    assert lib.gcwt_version() == 100
+    assert lib.gcwt_version() == 200
 
 
 def test_constants_match_header():
