@@ -130,7 +130,7 @@ int gcwt_plan_create(gcwt_plan** out, const gcwt_plan_desc* d) {
     p->out_kind = d->out_kind;
     p->device = d->device;
     p->flags = d->flags;
-    p->band_tol = d->band_tol > 0 ? d->band_tol : 3e-7;
+    p->band_tol = d->band_tol > 0 ? d->band_tol : 1e-7;
     p->guard_tol = d->guard_tol > 0 ? d->guard_tol : 5e-6;
     p->guard = d->compute_type == GCWT_F32 && !(d->flags & (GCWT_FLAG_NO_GUARD | GCWT_FLAG_FORCE_GENERIC));
     int off = 0;

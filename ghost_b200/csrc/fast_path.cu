@@ -440,6 +440,8 @@ static int guard_plan_build(gcwt_plan* p, const PlanResponses& pr, const std::ve
     GCWT_CUDA_OK(cudaMemcpy(p->d_guard_class, cls.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice));
     GCWT_CUDA_OK(cudaEventCreateWithFlags(&p->ev_guard, cudaEventDisableTiming));
     p->guard_last_flags.assign(S, 0);
+    p->guard_gain_h = gain;
+    p->guard_q_h = q;
     return GCWT_OK;
 }
 
@@ -686,10 +688,16 @@ pyramid_kernel(const TIn* __restrict__ in, int64_t in_stride, int64_t in_lo, int
             e_out += __shfl_xor_sync(0xffffffffu, e_out, o);
             if (FIRST) e_in += __shfl_xor_sync(0xffffffffu, e_in, o);
         }
-        if ((threadIdx.x & 31) == 0) {
+        __syncthreads();                                             // the tile is consumed: reuse ev as scratch
+        if ((threadIdx.x & 31) == 0) { ev[threadIdx.x >> 5] = e_out; if (FIRST) ev[8 + (threadIdx.x >> 5)] = e_in; }
+        __syncthreads();
+        if (threadIdx.x == 0) {                                      // one atomic per block and quantity
             double* a = acc + (int64_t)c * acc_stride;
-            if (e_out != 0.f) atomicAdd(a + level, (double)e_out);
-            if (FIRST && e_in != 0.f) atomicAdd(a, (double)e_in);
+            float so = 0.f, si = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { so += ev[w]; if (FIRST) si += ev[8 + w]; }
+            if (so != 0.f) atomicAdd(a + level, (double)so);
+            if (FIRST && si != 0.f) atomicAdd(a, (double)si);
         }
     }
 }
@@ -723,7 +731,10 @@ struct FusedParams {
     float ech_weight;         // chunk energy -> full-rate-equivalent energy of the segment (D * hop / chunk)
     float* pow;               // [channels][pow_stride] measured sum |W|^2 per scale
     int pow_stride;
-    float pow_weight;         // full / banded kernels sample a fraction of their outputs
+    float pow_weight;         // measured chunks -> all chunks (the guard measures every guard_every-th chunk)
+    int guard_every;
+    int q_mode;               // full kernel: 0 this launch covers every chunk; 1 only chunks q = i * guard_every (measured
+                              // launch); 2 all the others (n_chunks is then the number of chunks of THIS launch)
 };
 
 // e^{+2 pi i k / 4096} from the table of e^{-2 pi i k / 4096}
@@ -918,7 +929,7 @@ __device__ __forceinline__ void smem_fft4096_forward(float2* x, float2* y, const
 // smem: ex[2][4096] | Zs[kMaxClassScales][256] | Estep[256]
 constexpr size_t kBandedSmem = sizeof(float2) * (2 * 4096 + kMaxClassScales * kBins + kBins) + sizeof(int) * kMaxClassScales + 16;
 
-template <int KIND, int LP>       // LP > 0: compile-time log2(P) (store offsets become immediates)
+template <int KIND, int LP, bool GUARD>       // LP > 0: compile-time log2(P) (store offsets become immediates)
 __global__ void __launch_bounds__(256, 2)
 fused_banded_kernel(const FusedParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -940,6 +951,7 @@ fused_banded_kernel(const FusedParams prm) {
     const int64_t c = b / prm.n_chunks;
 
     const int64_t t0 = q * prm.hop - prm.offset;                 // full-rate index of chunk sample 0
+    const bool sample = GUARD && (q % prm.guard_every) == 0;     // accuracy guard: this chunk is measured (block-uniform)
     // ---- (1) forward FFT of the decimated chunk ---------------------------------
     {
         const float* src = (const float*)prm.src + c * prm.src_stride - prm.src_lo;
@@ -951,7 +963,7 @@ fused_banded_kernel(const FusedParams prm) {
             raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
         }
         const float cm = chunk_mean<kChunkDec / 256>(raw, (float*)Zs);
-        if (prm.acc != nullptr && unit == 0)
+        if (sample && unit == 0)
             chunk_energy_add<kChunkDec / 256>(raw, cm, (float*)Zs, prm.acc + c * prm.acc_stride + kGuardLevels + prm.class_idx,
                                               prm.ech_weight);
 #pragma unroll
@@ -992,7 +1004,7 @@ fused_banded_kernel(const FusedParams prm) {
     OutT* const out_c = (OutT*)prm.out + c * prm.c_stride + t0;
     int buf = 0;
     int pend = -1;                                                       // guard: scale whose counter is flushed after the next barrier
-    float* const pow_c = prm.pow ? prm.pow + c * prm.pow_stride : nullptr;
+    float* const pow_c = sample ? prm.pow + c * prm.pow_stride : nullptr;
     for (int it = 0; it < iters; ++it) {
         const int rel = col0 + it * 16 + r + (g << lp);                  // chunk-local sample of output k = 0
         const unsigned mask = valid_mask(rel, lp + 4, own_lo, own_hi);
@@ -1008,7 +1020,7 @@ fused_banded_kernel(const FusedParams prm) {
             for (int k = 1; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
             __syncthreads();
             if (pend >= 0 && tid == 0) {                                  // every add for scale `pend` came before this barrier
-                atomicAdd(pow_c + s_ids[pend], s_pow[pend & 1] * (float)iters);
+                atomicAdd(pow_c + s_ids[pend], s_pow[pend & 1] * (float)iters * prm.pow_weight);
                 s_pow[pend & 1] = 0.f;
             }
             pend = -1;
@@ -1017,7 +1029,7 @@ fused_banded_kernel(const FusedParams prm) {
             for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
             dft16<+1>(a);
             store_column<KIND>(out_c + (int64_t)s_ids[s] * prm.s_stride + rel, kstride, mask, a);
-            if (pow_c != nullptr && it == 0) {                            // sampled: the first column block of this unit
+            if (GUARD && pow_c != nullptr && it == 0) {                   // measured: the first column block of this unit
                 guard_pow_add<false>(a, mask, s_pow + (s & 1));
                 pend = s;
             }
@@ -1028,7 +1040,7 @@ fused_banded_kernel(const FusedParams prm) {
     }
     if (pend >= 0) {
         __syncthreads();
-        if (tid == 0) atomicAdd(pow_c + s_ids[pend], s_pow[pend & 1] * (float)iters);
+        if (tid == 0) atomicAdd(pow_c + s_ids[pend], s_pow[pend & 1] * (float)iters * prm.pow_weight);
     }
 }
 
@@ -1165,7 +1177,7 @@ __device__ __forceinline__ void interp_rows_wide(const float* __restrict__ pc, f
     }
 }
 
-template <int KIND>
+template <int KIND, bool GUARD>
 __global__ void __launch_bounds__(256, GCWT_INTERP_CTAS)
 fused_interp_kernel(const FusedParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1191,6 +1203,7 @@ fused_interp_kernel(const FusedParams prm) {
     const int64_t q = bid % prm.n_chunks;
     const int64_t c = bid / prm.n_chunks;
     const int64_t t0 = q * prm.hop - prm.offset;
+    const bool sample = GUARD && (q % prm.guard_every) == 0;     // accuracy guard: this chunk is measured (block-uniform)
 
     // this block's share of the chunk's owned output window, in coarse intervals
     const int lu = prm.log2u;
@@ -1211,7 +1224,7 @@ fused_interp_kernel(const FusedParams prm) {
             raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
         }
         const float cm = chunk_mean<kChunkDec / 256>(raw, (float*)Zs);
-        if (prm.acc != nullptr && split == 0)
+        if (sample && split == 0)
             chunk_energy_add<kChunkDec / 256>(raw, cm, (float*)Zs, prm.acc + c * prm.acc_stride + kGuardLevels + prm.class_idx,
                                               prm.ech_weight);
 #pragma unroll
@@ -1242,7 +1255,7 @@ fused_interp_kernel(const FusedParams prm) {
     float* const out_c = (float*)prm.out + c * prm.c_stride + t0;
     // guard: coarse samples (g + 16 k) * NCOL + col of this thread that lie in the block's own range
     unsigned own = 0;
-    if (prm.pow != nullptr) {
+    if (sample) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int iota = (g + 16 * k) * NCOL + col;
@@ -1268,14 +1281,14 @@ fused_interp_kernel(const FusedParams prm) {
         float* pc = Pc + sidx * PCS + g * NCOL + col;             // iota = (g + 16 k) * NCOL + col
 #pragma unroll
         for (int k = 0; k < 16; ++k) pc[k * 16 * NCOL] = a[k].x * a[k].x + a[k].y * a[k].y;
-        if (prm.pow != nullptr) guard_pow_add<true>(a, own, s_pow + sidx);
+        if (sample) guard_pow_add<true>(a, own, s_pow + sidx);
         __syncthreads();
         // (3) polyphase interpolation + epilogue for the scales of this pass
         // (dealing the (scale, interval) pairs of a pass to the threads as one flat sequence, to save the
         // partial last round of 256 per scale, measured slower: whole idle warps cost nothing)
         const int nsc = min(NSC, prm.n_scales - pair);
-        if (prm.pow != nullptr && tid < NSC) {                     // the loop's closing barrier orders the reset
-            if (tid < nsc) atomicAdd(prm.pow + c * prm.pow_stride + s_ids[pair + tid], s_pow[tid] * (float)(1 << lu));
+        if (sample && tid < NSC) {                                 // the loop's closing barrier orders the reset
+            if (tid < nsc) atomicAdd(prm.pow + c * prm.pow_stride + s_ids[pair + tid], s_pow[tid] * (float)(1 << lu) * prm.pow_weight);
             s_pow[tid] = 0.f;
         }
         for (int sl = 0; sl < nsc; ++sl) {
@@ -1349,7 +1362,7 @@ __device__ __forceinline__ void smem_fft2048_forward_low(float2* a, float2* b, c
     y1 = cadd(a[tid + 256], cmul(a[tid + 256 + N / 2], __ldg(tw + 2 * (tid + 256))));
 }
 
-template <int KIND>
+template <int KIND, bool GUARD>
 __global__ void __launch_bounds__(256, 2)
 fused_wide2_kernel(const FusedParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1370,6 +1383,7 @@ fused_wide2_kernel(const FusedParams prm) {
     const int own_hi = (int)min(prm.offset + prm.hop, prm.n - t0);
     const int ia = own_lo >> lu, ib = (own_hi + (1 << lu) - 1) >> lu;
     if (tid < prm.n_scales) s_ids[tid] = prm.scale_ids[tid];
+    const bool sample = GUARD && (q % prm.guard_every) == 0;     // accuracy guard: this chunk is measured (block-uniform)
 
     float2 y0, y1;                                                 // spectrum bins tid and tid + 256
     {
@@ -1383,7 +1397,7 @@ fused_wide2_kernel(const FusedParams prm) {
             raw[k] = (u >= prm.src_lo && u < prm.src_hi) ? src[u] : 0.f;
         }
         const float cm = chunk_mean<NV>(raw, (float*)(B1 + 3072));
-        if (prm.acc != nullptr)
+        if (sample)
             chunk_energy_add<NV>(raw, cm, (float*)(B1 + 3072), prm.acc + c * prm.acc_stride + kGuardLevels + prm.class_idx,
                                  prm.ech_weight);
 #pragma unroll
@@ -1403,7 +1417,7 @@ fused_wide2_kernel(const FusedParams prm) {
     float* const Pc = (float*)B1;
     const int col = r & 7, sidx = r >> 3;
     unsigned own = 0;                                              // guard: owned coarse samples (g + 16 k) * 8 + col
-    if (prm.pow != nullptr) {
+    if (sample) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int iota = (g + 16 * k) * 8 + col;
@@ -1447,11 +1461,11 @@ fused_wide2_kernel(const FusedParams prm) {
         float* pc = Pc + sidx * kPcStride + g * 8 + col;           // coarse index (g + 16 k) * 8 + col
 #pragma unroll
         for (int k = 0; k < 16; ++k) pc[k * 128] = a[k].x * a[k].x + a[k].y * a[k].y;
-        if (prm.pow != nullptr) guard_pow_add<true>(a, own, s_pow + sidx);
+        if (sample) guard_pow_add<true>(a, own, s_pow + sidx);
         __syncthreads();
-        if (prm.pow != nullptr && tid < 2) {                        // the loop's closing barrier orders the reset
+        if (sample && tid < 2) {                                    // the loop's closing barrier orders the reset
             if (pair + tid < prm.n_scales)
-                atomicAdd(prm.pow + c * prm.pow_stride + s_ids[pair + tid], s_pow[tid] * (float)(1 << lu));
+                atomicAdd(prm.pow + c * prm.pow_stride + s_ids[pair + tid], s_pow[tid] * (float)(1 << lu) * prm.pow_weight);
             s_pow[tid] = 0.f;
         }
         for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl) {
@@ -1484,7 +1498,60 @@ __device__ __forceinline__ void full_prepass(const float2* __restrict__ Yf, cons
     for (int k = 0; k < 16; ++k) A[tid * 17 + k] = k ? cmul(a[k], tw4k[k]) : a[k];
 }
 
-template <typename TIn, int KIND>
+// The per-scale loop of the full-spectrum kernel.  MEASURE: also accumulate the output energy of every scale
+// (accuracy guard); the flush path re-derives its pointer from the block index so that nothing extra stays live.
+template <int KIND, bool MEASURE>
+__device__ __forceinline__ void full_scale_loop(const FusedParams& prm, const float2* __restrict__ Yf, float2* __restrict__ ex,
+                                                float2* __restrict__ A, const int* s_ids, const int* s_nmu, float* s_pow,
+                                                const float2* tw, const float2* tw4k,
+                                                typename out_elem<KIND>::type* out_c, int rel, unsigned mask) {
+    const int tid = threadIdx.x;
+    const int r = tid & 15;
+    const int g = tid >> 4;
+    for (int s = 0; s < prm.n_scales; ++s) {
+        float2 a[16];
+        const int nmu = s_nmu[s];
+        // the table rows stream from L2 through L1: this kernel is co-limited by the LSU data pipe and
+        // the issue slots, not by this latency -- staging the rows ahead of time changed nothing
+        // measurable, neither with cp.async (a second LSU operation per entry) nor with a TMA bulk
+        // copy + mbarrier one scale ahead (8.89 vs 8.92 ms on config 2)
+        const float2* tab = prm.table + (int64_t)s * kFullN + tid;
+        if (nmu == 2) full_prepass<2>(Yf, tab, A, tw4k);
+        else if (nmu == 4) full_prepass<4>(Yf, tab, A, tw4k);
+        else if (nmu == 8) full_prepass<8>(Yf, tab, A, tw4k);
+        else full_prepass<16>(Yf, tab, A, tw4k);
+        __syncthreads();
+        if (MEASURE && s > 0 && tid == 0) {                          // every add for scale s - 1 came before this barrier
+            atomicAdd(prm.pow + (blockIdx.x / prm.n_chunks) * prm.pow_stride + s_ids[s - 1], s_pow[(s - 1) & 1] * prm.pow_weight);
+            s_pow[(s - 1) & 1] = 0.f;
+        }
+        // pass 1 of the 256-point transforms (16 columns)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 17 + r];
+        dft16<+1>(a);
+        float2* e = ex + (g * 16) * 16 + r;
+        e[0] = a[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
+        __syncthreads();
+        const float2* e2 = ex + g * 16 + r;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
+        dft16<+1>(a);
+        store_column<KIND>(out_c + (int64_t)s_ids[s] * prm.s_stride + rel, 256, mask, a);
+        if (MEASURE) guard_pow_add<false>(a, mask, s_pow + (s & 1));
+        // no trailing barrier: the next scale's pre-pass writes A, whose readers all passed
+        // the second barrier above; its pass 1 writes ex only after the next first barrier,
+        // which every thread reaches after finishing the reads of ex just done.
+    }
+    if (MEASURE) {
+        __syncthreads();
+        const int s = prm.n_scales - 1;
+        if (tid == 0) atomicAdd(prm.pow + (blockIdx.x / prm.n_chunks) * prm.pow_stride + s_ids[s], s_pow[s & 1] * prm.pow_weight);
+    }
+}
+
+template <typename TIn, int KIND, bool GUARD>
 __global__ void __launch_bounds__(256, 2)
 fused_full_kernel(const FusedParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1499,8 +1566,9 @@ fused_full_kernel(const FusedParams prm) {
     if (tid < 2) s_pow[tid] = 0.f;
     const int r = tid & 15;
     const int g = tid >> 4;
-    const int64_t q = blockIdx.x % prm.n_chunks;
+    const int64_t qi = blockIdx.x % prm.n_chunks;
     const int64_t c = blockIdx.x / prm.n_chunks;
+    const int64_t q = prm.q_mode == 0 ? qi : (prm.q_mode == 1 ? qi * prm.guard_every : qi + qi / (prm.guard_every - 1) + 1);
     const int64_t t0 = q * prm.hop - prm.offset;
 
     {
@@ -1520,7 +1588,7 @@ fused_full_kernel(const FusedParams prm) {
         for (int k = 0; k < kFullN / 256; ++k)                    // zero padding outside the readable range
             val[k] = (inside >> k & 1) ? (float)((double)raw[k] - mu) : 0.f;
         const float cm = chunk_mean<kFullN / 256>(val, (float*)ex + 2048);   // (behind the forward FFT's spill into ex)
-        if (prm.acc != nullptr)
+        if (GUARD)
             chunk_energy_add<kFullN / 256>(val, cm, (float*)ex + 2048, prm.acc + c * prm.acc_stride + kGuardLevels + prm.class_idx,
                                            prm.ech_weight);
 #pragma unroll
@@ -1539,63 +1607,29 @@ fused_full_kernel(const FusedParams prm) {
     const unsigned mask = valid_mask(rel, 8, (int)prm.offset, (int)min(prm.offset + prm.hop, prm.n - t0));
     OutT* const out_c = (OutT*)prm.out + c * prm.c_stride + t0;
     if (tid < prm.n_scales) { s_ids[tid] = prm.scale_ids[tid]; s_nmu[tid] = prm.scale_nmu[tid]; }
-    // guard: the output energy of every scale is measured on every fourth chunk (block-uniform)
-    float* const pow_c = (prm.pow != nullptr && (q & 3) == 0) ? prm.pow + c * prm.pow_stride : nullptr;
+    // accuracy guard: the output energy of every scale is measured on every guard_every-th chunk; those chunks
+    // run in a launch of their own (GUARD = true, q_mode 1) so that all the others run the plain kernel.
     __syncthreads();
-    for (int s = 0; s < prm.n_scales; ++s) {
-        float2 a[16];
-        const int nmu = s_nmu[s];
-        // the table rows stream from L2 through L1: this kernel is co-limited by the LSU data pipe and
-        // the issue slots, not by this latency -- staging the rows ahead of time changed nothing
-        // measurable, neither with cp.async (a second LSU operation per entry) nor with a TMA bulk
-        // copy + mbarrier one scale ahead (8.89 vs 8.92 ms on config 2)
-        const float2* tab = prm.table + (int64_t)s * kFullN + tid;
-        if (nmu == 2) full_prepass<2>(Yf, tab, A, tw4k);
-        else if (nmu == 4) full_prepass<4>(Yf, tab, A, tw4k);
-        else if (nmu == 8) full_prepass<8>(Yf, tab, A, tw4k);
-        else full_prepass<16>(Yf, tab, A, tw4k);
-        __syncthreads();
-        if (pow_c != nullptr && s > 0 && tid == 0) {                 // every add for scale s - 1 came before this barrier
-            atomicAdd(pow_c + s_ids[s - 1], s_pow[(s - 1) & 1] * prm.pow_weight);
-            s_pow[(s - 1) & 1] = 0.f;
-        }
-        // pass 1 of the 256-point transforms (16 columns)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = A[(g + 16 * i) * 17 + r];
-        dft16<+1>(a);
-        float2* e = ex + (g * 16) * 16 + r;
-        e[0] = a[0];
-#pragma unroll
-        for (int k = 1; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
-        __syncthreads();
-        const float2* e2 = ex + g * 16 + r;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
-        dft16<+1>(a);
-        store_column<KIND>(out_c + (int64_t)s_ids[s] * prm.s_stride + rel, 256, mask, a);
-        if (pow_c != nullptr) guard_pow_add<false>(a, mask, s_pow + (s & 1));
-        // no trailing barrier: the next scale's pre-pass writes A, whose readers all passed
-        // the second barrier above; its pass 1 writes ex only after the next first barrier,
-        // which every thread reaches after finishing the reads of ex just done.
-    }
-    if (pow_c != nullptr) {
-        __syncthreads();
-        const int s = prm.n_scales - 1;
-        if (tid == 0) atomicAdd(pow_c + s_ids[s], s_pow[s & 1] * prm.pow_weight);
-    }
+    full_scale_loop<KIND, GUARD>(prm, Yf, ex, A, s_ids, s_nmu, s_pow, tw, tw4k, out_c, rel, mask);
 }
 
 // ============================================================================ driver
-template <int KIND, int LP>
-static void launch_banded_one(unsigned nblk, cudaStream_t st, const FusedParams& prm) {
+template <int KIND, int LP, bool GUARD>
+static void launch_banded_g(unsigned nblk, cudaStream_t st, const FusedParams& prm) {
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaFuncSetAttribute(fused_banded_kernel<KIND, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem);
+        cudaFuncSetAttribute(fused_banded_kernel<KIND, LP, GUARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandedSmem);
         attr_set[dev & 63] = true;
     }
-    fused_banded_kernel<KIND, LP><<<nblk, 256, kBandedSmem, st>>>(prm);
+    fused_banded_kernel<KIND, LP, GUARD><<<nblk, 256, kBandedSmem, st>>>(prm);
+}
+
+template <int KIND, int LP>
+static void launch_banded_one(unsigned nblk, cudaStream_t st, const FusedParams& prm) {
+    if (prm.pow != nullptr) launch_banded_g<KIND, LP, true>(nblk, st, prm);
+    else launch_banded_g<KIND, LP, false>(nblk, st, prm);
 }
 
 static void launch_banded(int kind, int lp, unsigned nblk, cudaStream_t st, const FusedParams& prm) {
@@ -1611,23 +1645,29 @@ static void launch_banded(int kind, int lp, unsigned nblk, cudaStream_t st, cons
     }
 }
 
-template <typename TIn, int KIND>
-static void launch_full_kind(unsigned nblk, cudaStream_t st, const FusedParams& prm) {
+template <typename TIn, int KIND, bool GUARD>
+static void launch_full_g(unsigned nblk, cudaStream_t st, const FusedParams& prm) {
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaFuncSetAttribute(fused_full_kernel<TIn, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem);
+        cudaFuncSetAttribute(fused_full_kernel<TIn, KIND, GUARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFullSmem);
         attr_set[dev & 63] = true;
     }
-    fused_full_kernel<TIn, KIND><<<nblk, 256, kFullSmem, st>>>(prm);
+    fused_full_kernel<TIn, KIND, GUARD><<<nblk, 256, kFullSmem, st>>>(prm);
+}
+
+template <typename TIn, int KIND>
+static void launch_full_kind(unsigned nblk, cudaStream_t st, const FusedParams& prm, bool measure) {
+    if (measure) launch_full_g<TIn, KIND, true>(nblk, st, prm);
+    else launch_full_g<TIn, KIND, false>(nblk, st, prm);
 }
 
 template <typename TIn>
-static void launch_full(int kind, unsigned nblk, cudaStream_t st, const FusedParams& prm) {
-    if (kind == GCWT_OUT_COMPLEX) launch_full_kind<TIn, GCWT_OUT_COMPLEX>(nblk, st, prm);
-    else if (kind == GCWT_OUT_AMPLITUDE) launch_full_kind<TIn, GCWT_OUT_AMPLITUDE>(nblk, st, prm);
-    else launch_full_kind<TIn, GCWT_OUT_POWER>(nblk, st, prm);
+static void launch_full(int kind, unsigned nblk, cudaStream_t st, const FusedParams& prm, bool measure) {
+    if (kind == GCWT_OUT_COMPLEX) launch_full_kind<TIn, GCWT_OUT_COMPLEX>(nblk, st, prm, measure);
+    else if (kind == GCWT_OUT_AMPLITUDE) launch_full_kind<TIn, GCWT_OUT_AMPLITUDE>(nblk, st, prm, measure);
+    else launch_full_kind<TIn, GCWT_OUT_POWER>(nblk, st, prm, measure);
 }
 
 struct LevelGeom { int64_t lo, hi, len, stride; float* ptr; };
@@ -1714,12 +1754,20 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prm.out = out; prm.s_stride = s_stride; prm.c_stride = c_stride;
         prm.inv_nc = 1.0f / (float)fc.nc_full;
         prm.log2u = fc.log2u; prm.coef = fc.d_coef; prm.twf = p->d_twiddle; prm.scale_nmu = fc.d_scale_nmu;
+        prm.q_mode = 0;
         prm.acc = guard ? p->d_guard_acc : nullptr; prm.acc_stride = acc_stride;
         prm.class_idx = (int)(&fc - p->classes.data());
         prm.pow = guard ? p->d_guard_pow : nullptr; prm.pow_stride = p->n_scales;
-        prm.pow_weight = 1.f;
-        // chunk energy -> energy of the segment at the full rate: D samples per decimated one, chunks overlap
-        prm.ech_weight = (float)((double)(fc.level >= 0 ? (int64_t(1) << fc.level) : 1) * (double)fc.hop / (double)fc.nc_full);
+        // the guard measures every guard_every-th chunk of a long segment (block-uniform choice in the kernels)
+        auto set_guard_sampling = [&](int64_t n_chunks, int every, double chunk_to_rate) {
+            prm.guard_every = n_chunks >= 64 ? every : 1;
+            const double w = (double)n_chunks / (double)((n_chunks + prm.guard_every - 1) / prm.guard_every);
+            prm.pow_weight = (float)w;
+            // chunk energy -> energy of the segment at the full rate: D samples per decimated one, chunks overlap
+            prm.ech_weight = (float)(w * chunk_to_rate);
+        };
+        set_guard_sampling(prm.n_chunks, fc.level >= 0 ? 4 : 8,
+                           (double)(fc.level >= 0 ? (int64_t(1) << fc.level) : 1) * (double)fc.hop / (double)fc.nc_full);
         if (fc.level >= 0 && fc.interp && fc.wide && fc.d_table2) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1727,15 +1775,18 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.offset = fc.offset2; prm.hop = fc.hop2;
             prm.n_chunks = (n + fc.hop2 - 1) / fc.hop2;
             prm.table = fc.d_table2;
-            prm.ech_weight = (float)((double)(int64_t(1) << fc.level) * (double)fc.hop2 / (double)(2 * fc.nc_full));
+            set_guard_sampling(prm.n_chunks, 4, (double)(int64_t(1) << fc.level) * (double)fc.hop2 / (double)(2 * fc.nc_full));
             prm.p_cols = 8; prm.log2p = 3; prm.units_per_chunk = 1;
             prm.iters = rows_aligned ? 1 : 0;                      // 128-bit stores allowed
             const int64_t nblk = n_channels * prm.n_chunks;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
-            if (p->out_kind == GCWT_OUT_AMPLITUDE)
-                fused_wide2_kernel<GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kWide2Smem, cs>>>(prm);
-            else
-                fused_wide2_kernel<GCWT_OUT_POWER><<<(unsigned)nblk, 256, kWide2Smem, cs>>>(prm);
+            if (p->out_kind == GCWT_OUT_AMPLITUDE) {
+                if (guard) fused_wide2_kernel<GCWT_OUT_AMPLITUDE, true><<<(unsigned)nblk, 256, kWide2Smem, cs>>>(prm);
+                else fused_wide2_kernel<GCWT_OUT_AMPLITUDE, false><<<(unsigned)nblk, 256, kWide2Smem, cs>>>(prm);
+            } else {
+                if (guard) fused_wide2_kernel<GCWT_OUT_POWER, true><<<(unsigned)nblk, 256, kWide2Smem, cs>>>(prm);
+                else fused_wide2_kernel<GCWT_OUT_POWER, false><<<(unsigned)nblk, 256, kWide2Smem, cs>>>(prm);
+            }
         } else if (uses_interp(fc)) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1753,10 +1804,13 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.units_per_chunk = (int)splits;
             const int64_t nblk = chunks * splits;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
-            if (p->out_kind == GCWT_OUT_AMPLITUDE)
-                fused_interp_kernel<GCWT_OUT_AMPLITUDE><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
-            else
-                fused_interp_kernel<GCWT_OUT_POWER><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
+            if (p->out_kind == GCWT_OUT_AMPLITUDE) {
+                if (guard) fused_interp_kernel<GCWT_OUT_AMPLITUDE, true><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
+                else fused_interp_kernel<GCWT_OUT_AMPLITUDE, false><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
+            } else {
+                if (guard) fused_interp_kernel<GCWT_OUT_POWER, true><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
+                else fused_interp_kernel<GCWT_OUT_POWER, false><<<(unsigned)nblk, 256, kInterpSmem, cs>>>(prm);
+            }
         } else if (fc.level >= 0) {
             const LevelGeom& g = lv[fc.level];
             prm.src = g.ptr; prm.src_stride = g.stride; prm.src_lo = g.lo; prm.src_hi = g.hi;
@@ -1774,8 +1828,19 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.log2d = 0; prm.p_cols = 16; prm.log2p = 4; prm.iters = 1; prm.units_per_chunk = 1;
             const int64_t nblk = n_channels * prm.n_chunks;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
-            prm.pow_weight = (float)((double)prm.n_chunks / (double)((prm.n_chunks + 3) / 4));   // every fourth chunk is measured
-            launch_full<TIn>(p->out_kind, (unsigned)nblk, cs, prm);
+            if (!guard) {
+                launch_full<TIn>(p->out_kind, (unsigned)nblk, cs, prm, false);
+            } else {
+                // measured chunks (every guard_every-th) and the others in two launches of two kernels
+                const int64_t n_all = prm.n_chunks, n_meas = (n_all + prm.guard_every - 1) / prm.guard_every;
+                if (n_all > n_meas) {
+                    prm.q_mode = 2; prm.n_chunks = n_all - n_meas;
+                    launch_full<TIn>(p->out_kind, (unsigned)(n_channels * prm.n_chunks), cs, prm, false);
+                    count_launch();
+                }
+                prm.q_mode = prm.guard_every > 1 ? 1 : 0; prm.n_chunks = n_meas;
+                launch_full<TIn>(p->out_kind, (unsigned)(n_channels * prm.n_chunks), cs, prm, true);
+            }
         }
         count_launch();
         prof_end(p, sp, cs);
@@ -1880,30 +1945,55 @@ int guard_resolve(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, 
     std::fill(p->guard_last_flags.begin(), p->guard_last_flags.end(), 0);
     const size_t in_el = in_type == GCWT_F32 ? 4 : 8;
     const size_t out_el = p->out_kind == GCWT_OUT_COMPLEX ? 8 : 4;
-    if (getenv("GCWT_GUARD_DUMP")) {                               // developer aid: the measured energies of channel 0
-        std::vector<double> a(acc_stride);
-        std::vector<float> pw(S);
-        cudaMemcpy(a.data(), p->d_guard_acc, sizeof(double) * acc_stride, cudaMemcpyDeviceToHost);
-        cudaMemcpy(pw.data(), p->d_guard_pow, sizeof(float) * S, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "gcwt guard e_j:");
-        for (int j = 0; j < kGuardLevels; ++j) fprintf(stderr, " %.3e", std::ldexp(a[j], j));
-        fprintf(stderr, "\ngcwt guard chunk energies:");
-        for (int j = kGuardLevels; j < acc_stride; ++j) fprintf(stderr, " %.3e", a[j]);
-        fprintf(stderr, "\ngcwt guard pow:");
-        for (int s2 = 0; s2 < S; ++s2) fprintf(stderr, " %.3e", pw[s2]);
-        fprintf(stderr, "\n");
+    if (getenv("GCWT_GUARD_DUMP")) {       // developer aid: what made the guard fire, per flagged pair (first 12)
+        std::vector<double> a((size_t)acc_stride * n_channels);
+        std::vector<float> pw((size_t)S * n_channels);
+        cudaMemcpy(a.data(), p->d_guard_acc, sizeof(double) * a.size(), cudaMemcpyDeviceToHost);
+        cudaMemcpy(pw.data(), p->d_guard_pow, sizeof(float) * pw.size(), cudaMemcpyDeviceToHost);
+        int shown = 0;
+        const double eps = 5.9604644775390625e-08;
+        for (int64_t c = 0; c < n_channels && shown < 12; ++c)
+            for (int s2 = 0; s2 < S && shown < 12; ++s2) {
+                if (!p->h_guard_flags[c * S + s2]) continue;
+                ++shown;
+                const double* ac = a.data() + c * acc_stride;
+                const int lev = p->scales[s2].level, ci = [&] { for (size_t k = 0; k < p->classes.size(); ++k) for (int id : p->classes[k].scale_ids) if (id == s2) return (int)k; return 0; }();
+                const double P = pw[c * S + s2], qs = p->guard_q_h[s2];
+                fprintf(stderr, "gcwt guard: n=%lld ch %lld scale %d level %d L %lld: P %.3e  round %.2e", (long long)n_samples, (long long)c, s2, lev,
+                        (long long)p->scales[s2].L, P, std::sqrt(kGuardKRound * eps * kGuardKRound * eps * qs * ac[kGuardLevels + ci] / P));
+                if (lev >= 0) {
+                    double stage = 0.0;
+                    for (int j = 1; j <= lev; ++j) stage += std::ldexp(ac[j], j + j - lev);
+                    fprintf(stderr, "  stage %.2e  band:", std::sqrt(kGuardKStage * eps * kGuardKStage * eps * qs * stage / 3.0 / P));
+                    for (int b = 0; b <= lev + 1; ++b) {
+                        const double e_lo = (b <= lev && b + 2 < kGuardLevels) ? std::ldexp(ac[b + 2], b + 2) : 0.0;
+                        const double eb = std::max(std::ldexp(ac[b], b) - e_lo, 0.0);
+                        fprintf(stderr, " %.1e", std::sqrt(p->guard_gain_h[(size_t)s2 * kGuardSlots + b] * eb / P));
+                    }
+                }
+                fprintf(stderr, "\n");
+            }
     }
-    for (int64_t c = 0; c < n_channels; ++c) {
-        std::vector<int> ids;
-        for (int s2 = 0; s2 < S; ++s2)
-            if (p->h_guard_flags[c * S + s2]) { ids.push_back(s2); p->guard_last_flags[s2] = 1; }
-        if (ids.empty()) continue;
+    // runs of consecutive channels with the same failing scales are re-computed together
+    std::vector<int> ids, run_ids;
+    int64_t run_start = 0;
+    for (int64_t c = 0; c <= n_channels; ++c) {
+        ids.clear();
+        if (c < n_channels)
+            for (int s2 = 0; s2 < S; ++s2)
+                if (p->h_guard_flags[c * S + s2]) { ids.push_back(s2); p->guard_last_flags[s2] = 1; }
         p->guard_last += (int64_t)ids.size();
-        const int sp = prof_begin(p, 3, st);
-        int rc = generic_execute(p, ids, (const char*)x + in_el * c * x_stride, in_type, 1, n_samples, x_stride, halo_l, halo_r,
-                                 d_means + c, (char*)out + out_el * c * c_stride, s_stride, c_stride, st, true);
-        prof_end(p, sp, st);
-        if (rc) return rc;
+        if (c < n_channels && c > run_start && ids == run_ids) continue;
+        if (c > run_start && !run_ids.empty()) {
+            const int sp = prof_begin(p, 3, st);
+            int rc = generic_execute(p, run_ids, (const char*)x + in_el * run_start * x_stride, in_type, c - run_start, n_samples,
+                                     x_stride, halo_l, halo_r, d_means + run_start, (char*)out + out_el * run_start * c_stride,
+                                     s_stride, c_stride, st, true);
+            prof_end(p, sp, st);
+            if (rc) return rc;
+        }
+        run_start = c;
+        run_ids = ids;
     }
     p->guard_total += p->guard_last;
     return GCWT_OK;
@@ -1913,10 +2003,14 @@ static bool g_attr_done[64] = {false};
 
 template <typename TIn>
 static int set_smem_attrs() {
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_wide2_kernel<GCWT_OUT_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWide2Smem));
-    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_wide2_kernel<GCWT_OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWide2Smem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_wide2_kernel<GCWT_OUT_AMPLITUDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWide2Smem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_wide2_kernel<GCWT_OUT_POWER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWide2Smem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_AMPLITUDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_interp_kernel<GCWT_OUT_POWER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInterpSmem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_wide2_kernel<GCWT_OUT_AMPLITUDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWide2Smem));
+    GCWT_CUDA_OK(cudaFuncSetAttribute(fused_wide2_kernel<GCWT_OUT_POWER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWide2Smem));
     return GCWT_OK;
 }
 

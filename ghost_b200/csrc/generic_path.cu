@@ -177,7 +177,8 @@ static int generic_run(gcwt_plan* p, const std::vector<int>& ids, const TIn* x, 
 
     const size_t row = (size_t)nfft * sizeof(C);
     const size_t budget = (size_t)1 << 30;
-    int ib = (int)std::min<int64_t>(n_items, 4);
+    // few scales (the accuracy guard re-computing a handful of pairs): batch more chunks per launch instead
+    int ib = (int)std::min<int64_t>(n_items, std::max<int64_t>(4, std::min<int64_t>(32, (int64_t)(budget / (6 * row * std::min(ns, 4))))));
     int sb = (int)std::min<int64_t>(ns, std::max<int64_t>(1, (int64_t)(budget / (2 * row * ib))));
     sb = std::min(sb, 1024);
     // layout: Y[ib] | H[sb] | Za[ib*sb] | Zb[ib*sb] | ids[ns] | Yscratch[ib]

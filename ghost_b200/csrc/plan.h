@@ -91,7 +91,7 @@ struct gcwt_plan {
     int out_kind = GCWT_OUT_AMPLITUDE;
     int device = 0;
     int flags = 0;
-    double band_tol = 3e-7;
+    double band_tol = 1e-7;
     std::vector<gcwt::ScaleInfo> scales;
     std::vector<double> terms;
     gcwt::ScaleInfo* d_scales = nullptr;
@@ -129,6 +129,7 @@ struct gcwt_plan {
     cudaEvent_t ev_guard = nullptr;
     int64_t guard_last = 0, guard_total = 0, guard_checked = 0;   // re-computed (channel, scale) pairs
     std::vector<unsigned char> guard_last_flags;                  // any-channel flag per scale of the last call
+    std::vector<float> guard_gain_h, guard_q_h;                   // host copies of the tables (diagnostics)
 };
 
 namespace gcwt {

@@ -57,7 +57,7 @@ class ContinuousWaveletTransform(WaveletTransform):
         CUDA device ordinal.  Default 0.
     band_tol : float, optional
         float32 only: out-of-band filter energy (amplitude ratio) the band-limited kernels may drop.
-        Default 3e-7.
+        Default 1e-7.
     guard : bool, optional
         float32 only: measure, per call, whether the recording's spectrum lets the float32 kernels hold
         the 1e-5 bar for every (channel, scale) and re-compute the ones that cannot in float64

@@ -71,7 +71,7 @@ typedef struct gcwt_plan_desc {
     int32_t        device;       /* CUDA device ordinal                                           */
     int32_t        flags;        /* GCWT_FLAG_*                                                   */
     double         band_tol;     /* fp32 fast path: allowed out-of-band filter energy (amplitude
-                                    ratio); 0 selects the default 3e-7                            */
+                                    ratio); 0 selects the default 1e-7                            */
     double         guard_tol;    /* fp32 accuracy guard: largest tolerated bound on a scale's relative
                                     L2 error before it is re-computed in fp64; 0 selects 5e-6      */
 } gcwt_plan_desc;
