@@ -176,6 +176,7 @@ int gcwt_plan_destroy(gcwt_plan* p) {
     if (!p) return GCWT_OK;
     cudaSetDevice(p->device);
     prof_collect(p);
+    host_stage_free(p);
     fast_plan_free(p);
     if (p->d_scales) cudaFree(p->d_scales);
     if (p->d_terms) cudaFree(p->d_terms);
@@ -302,46 +303,22 @@ int gcwt_execute(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_channel
 }
 
 int gcwt_execute_host(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_channels,
-                      int64_t n_samples, int64_t x_stride, const double* means_host, void* out,
-                      int64_t out_scale_stride, int64_t out_channel_stride) {
+                      int64_t n_samples, int64_t x_stride, const int64_t* epoch_bounds, int32_t n_epochs,
+                      const double* means_host, void* out, int64_t out_scale_stride, int64_t out_channel_stride) {
     int rc = check_exec_args(p, x, in_type, n_channels, n_samples, x_stride, out);
     if (rc) return rc;
+    if (out_scale_stride < n_samples) { set_error("execute_host: out_scale_stride smaller than n_samples"); return GCWT_ERR_ARG; }
     GCWT_CUDA_OK(cudaSetDevice(p->device));
-    const size_t in_el = in_type == GCWT_F32 ? 4 : 8;
-    size_t out_el = p->compute_type == GCWT_F32 ? 4 : 8;
-    if (p->out_kind == GCWT_OUT_COMPLEX) out_el *= 2;
-    // device staging uses dense strides
-    const int64_t d_s = n_samples, d_c = n_samples * p->n_scales;
-    void *d_x = nullptr, *d_out = nullptr;
-    double* d_means = nullptr;
-    cudaError_t e = cudaMalloc(&d_x, in_el * n_samples * n_channels);
-    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_el * (size_t)d_c * n_channels);
-    if (e == cudaSuccess && means_host) e = cudaMalloc((void**)&d_means, sizeof(double) * n_channels);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        if (d_x) cudaFree(d_x);
-        if (d_out) cudaFree(d_out);
-        set_error(std::string("execute_host: device allocation failed: ") + cudaGetErrorString(e));
-        return GCWT_ERR_NOMEM;
-    }
-    rc = GCWT_OK;
-    e = cudaMemcpy2D(d_x, in_el * n_samples, x, in_el * x_stride, in_el * n_samples, n_channels, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && means_host) e = cudaMemcpy(d_means, means_host, sizeof(double) * n_channels, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { set_error(std::string("execute_host: H2D failed: ") + cudaGetErrorString(e)); rc = GCWT_ERR_CUDA; }
-    if (rc == GCWT_OK)
-        rc = gcwt_execute(p, d_x, in_type, n_channels, n_samples, n_samples, 0, 0, d_means, d_out, d_s, d_c, nullptr);
-    if (rc == GCWT_OK) {
-        e = cudaDeviceSynchronize();
-        for (int64_t c = 0; c < n_channels && e == cudaSuccess; ++c)
-            e = cudaMemcpy2D((char*)out + out_el * c * out_channel_stride, out_el * out_scale_stride,
-                             (char*)d_out + out_el * c * d_c, out_el * d_s, out_el * n_samples, p->n_scales,
-                             cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) { set_error(std::string("execute_host: D2H failed: ") + cudaGetErrorString(e)); rc = GCWT_ERR_CUDA; }
-    }
-    cudaFree(d_x);
-    cudaFree(d_out);
-    if (d_means) cudaFree(d_means);
-    return rc;
+    int64_t tile_hint = 0;
+    if (const char* e = getenv("GCWT_HOST_TILE")) tile_hint = atoll(e);       // developer aid: force the time tile
+    return host_execute(p, x, in_type, n_channels, n_samples, x_stride, epoch_bounds, n_epochs, means_host, out,
+                        out_scale_stride, out_channel_stride, tile_hint);
+}
+
+int gcwt_host_stats(const gcwt_plan* p, double* out4) {
+    if (!p || !out4) { set_error("host_stats: NULL argument"); return GCWT_ERR_ARG; }
+    for (int k = 0; k < 4; ++k) out4[k] = p->host.last_ms[k];
+    return GCWT_OK;
 }
 
 int gcwt_interp_taps(int32_t log2_u, int32_t n_taps, double oversampling, float* out_host) {

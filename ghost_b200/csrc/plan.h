@@ -130,6 +130,16 @@ struct gcwt_plan {
     int64_t guard_last = 0, guard_total = 0, guard_checked = 0;   // re-computed (channel, scale) pairs
     std::vector<unsigned char> guard_last_flags;                  // any-channel flag per scale of the last call
     std::vector<float> guard_gain_h, guard_q_h;                   // host copies of the tables (diagnostics)
+    // host-buffer path (gcwt_execute_host): persistent staging, grown on demand
+    struct HostStage {
+        void* d_in = nullptr; size_t in_bytes = 0;           // the channel group's samples
+        void* d_out[2] = {nullptr, nullptr}; size_t out_bytes = 0;   // double-buffered result tiles
+        void* h_ring[2] = {nullptr, nullptr}; size_t ring_bytes = 0; // pinned bounce buffers (pageable destinations only)
+        double* d_means = nullptr; int64_t means_cap = 0;
+        cudaStream_t st_compute = nullptr, st_copy = nullptr;
+        cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+        double last_ms[4] = {0, 0, 0, 0};                   // wall, h2d, tiles, bytes out (diagnostics)
+    } host;
 };
 
 namespace gcwt {
@@ -159,4 +169,8 @@ void fast_plan_free(gcwt_plan* p);
 int means_blocks(int64_t n_samples);
 int means_launch(const void* x, int in_type, int64_t n_channels, int64_t n_samples,
                  int64_t x_stride, double* d_means, double* partial, cudaStream_t st);
+int host_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, int64_t n_samples, int64_t x_stride,
+                 const int64_t* epochs, int n_epochs, const double* means_host, void* out, int64_t s_stride,
+                 int64_t c_stride, int64_t tile_hint);
+void host_stage_free(gcwt_plan* p);
 }  // namespace gcwt

@@ -183,29 +183,55 @@ class CwtPlan:
             done += (b - a) * n_ch * self.n_scales
         return done
 
-    def execute_host(self, x, out=None, means=None):
-        """Host-buffer entry point (numpy in, numpy out) through gcwt_execute_host."""
-        x = np.ascontiguousarray(x)
+    def execute_host(self, x, out=None, means=None, epochs=None):
+        """Host-buffer entry point (numpy in, numpy out) through gcwt_execute_host: the whole transform
+        body of the reference (global mean removal, one zero-padded convolution per epoch, zeros outside
+        the epochs; transforms.py:142-143,185,202-204) as one streamed, double-buffered call.
+
+        ``x`` (channels, samples) or (samples,); ``out`` optional (channels, scales, samples) array of the
+        plan's output dtype with unit sample stride -- pass a pinned one (e.g. the numpy view of a
+        ``torch.empty(..., pin_memory=True)``) to let the device write it by DMA; ``epochs`` optional
+        (E, 2) array of [start, stop) sample bounds.  Results larger than device memory are fine."""
+        x = np.asarray(x)
         if x.ndim == 1:
             x = x[None, :]
-        if x.dtype not in (np.float32, np.float64):
+        if x.ndim != 2:
+            raise ValueError("x must be (channels, samples)")
+        if x.dtype not in (np.float32, np.float64) or (self.dtype == np.float64 and x.dtype != np.float64):
             x = x.astype(np.float64)
+        if x.strides[1] != x.itemsize:
+            x = np.ascontiguousarray(x)
         n_ch, n = x.shape
         if self.output == "complex":
-            odt = np.complex64 if self.dtype == np.float32 else np.complex128
+            odt = np.dtype(np.complex64 if self.dtype == np.float32 else np.complex128)
         else:
             odt = self.dtype
         if out is None:
             out = np.empty((n_ch, self.n_scales, n), dtype=odt)
-        assert out.dtype == odt and out.flags.c_contiguous and out.shape == (n_ch, self.n_scales, n)
+        if out.dtype != odt or out.shape != (n_ch, self.n_scales, n) or out.strides[2] != out.itemsize \
+                or out.strides[0] % out.itemsize or out.strides[1] % out.itemsize:
+            raise ValueError("out must be (channels, scales, samples) of dtype %s with unit sample stride" % odt)
         mptr = None
         if means is not None:
             means = np.ascontiguousarray(means, dtype=np.float64)
+            if means.size != n_ch:
+                raise ValueError("means must hold one value per channel")
             mptr = means.ctypes.data
+        eptr, n_ep = None, 0
+        if epochs is not None:
+            epochs = np.ascontiguousarray(epochs, dtype=np.int64).reshape(-1, 2)
+            eptr, n_ep = epochs.ctypes.data, int(epochs.shape[0])
         in_type = _lib.F32 if x.dtype == np.float32 else _lib.F64
         _lib.check(self.lib.gcwt_execute_host(self._h, x.ctypes.data, in_type, n_ch, n, x.strides[0] // x.itemsize,
-                                              mptr, out.ctypes.data, n, n * self.n_scales))
+                                              eptr, n_ep, mptr, out.ctypes.data, out.strides[1] // out.itemsize,
+                                              out.strides[0] // out.itemsize))
         return out
+
+    def host_stats(self):
+        """{wall_ms, pinned_destination, tiles, bytes_out} of the last execute_host."""
+        v = (C.c_double * 4)()
+        _lib.check(self.lib.gcwt_host_stats(self._h, v))
+        return {"wall_ms": float(v[0]), "pinned_destination": bool(v[1]), "tiles": int(v[2]), "bytes_out": int(v[3])}
 
     PROFILE_KINDS = ("mean+pyramid", "fused_full", "fused_banded", "generic", "fused_interp")
 

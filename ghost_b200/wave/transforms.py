@@ -138,7 +138,7 @@ class ContinuousWaveletTransform(WaveletTransform):
     # ------------------------------------------------------------------ transform
     def transform(self, data, *, timestamps=None, fs=None, freq_limits=None, freqs=None,
                   voices_per_octave=None, parallel=None, verbose=None, multichannel=None,
-                  keep_on_device=None, **kwargs):
+                  keep_on_device=None, out=None, **kwargs):
         """Continuous wavelet transform of one recording.
 
         Parameters as the reference (transforms.py:59-106): ``data`` is an ndarray with
@@ -151,11 +151,13 @@ class ContinuousWaveletTransform(WaveletTransform):
         always processes all scales at once).
 
         ``multichannel=True`` accepts a (channels, samples) ndarray; results then have
-        shape (channels, scales, samples).
+        shape (channels, scales, samples).  ``out`` is an optional preallocated result array
+        ((scales, samples), or (channels, scales, samples) with ``multichannel``) of the output dtype;
+        a pinned one is written by DMA.  ``keep_on_device=True`` leaves the result on the GPU instead
+        (``device_result``; it must then fit in device memory).
 
         Returns None; results are read from the properties.
         """
-        import torch
         if multichannel is None:
             multichannel = False
         if multichannel:
@@ -214,31 +216,42 @@ class ContinuousWaveletTransform(WaveletTransform):
             return
         plan = self._get_plan(frequencies)
 
-        dev = torch.device("cuda", self._device)
         in_dtype = np.float32 if (x_host.dtype == np.float32 and self._dtype == np.float32) else np.float64
-        x_dev = torch.from_numpy(np.ascontiguousarray(x_host, dtype=in_dtype)).to(dev)
+        self._multichannel = bool(multichannel)
+        self._host = None
+        self._result = None
         start_time = _time.time()
-        means = plan.channel_means(x_dev)                  # global mean, transforms.py:142-143
-        out = plan.alloc_out(x_dev.shape[0], x_dev.shape[1])
-        covered = 0
-        for start, stop in epoch_bounds:                   # transforms.py:202-204
-            plan.execute(x_dev, out, means=means, start=int(start), stop=int(stop))
-            covered += int(stop) - int(start)
-        if covered != x_dev.shape[1]:
-            out_mask = torch.ones(x_dev.shape[1], dtype=torch.bool, device=dev)
-            for start, stop in epoch_bounds:
-                out_mask[int(start):int(stop)] = False
-            out[:, :, out_mask] = 0
-        if verbose:
+        if not keep_on_device:
+            # host arrays in, host arrays out (what the reference returns, transforms.py:185,231): one
+            # streamed call into the library -- tiles of the result travel to the host while the next is
+            # computed, so results larger than device memory work
+            x_in = x_host if x_host.dtype == in_dtype else x_host.astype(in_dtype)
+            if out is not None:
+                res = out if multichannel else out[None]
+            else:
+                res = None
+            res = plan.execute_host(x_in, out=res, epochs=epoch_bounds)
+            self._host = res if multichannel else res[0]
+        else:
+            import torch
+            dev = torch.device("cuda", self._device)
+            x_dev = torch.from_numpy(np.ascontiguousarray(x_host, dtype=in_dtype)).to(dev)
+            means = plan.channel_means(x_dev)                  # global mean, transforms.py:142-143
+            res = plan.alloc_out(x_dev.shape[0], x_dev.shape[1])
+            covered = 0
+            for start, stop in epoch_bounds:                   # transforms.py:202-204
+                plan.execute(x_dev, res, means=means, start=int(start), stop=int(stop))
+                covered += int(stop) - int(start)
+            if covered != x_dev.shape[1]:
+                out_mask = torch.ones(x_dev.shape[1], dtype=torch.bool, device=dev)
+                for start, stop in epoch_bounds:
+                    out_mask[int(start):int(stop)] = False
+                res[:, :, out_mask] = 0
             torch.cuda.synchronize(dev)
+            self._result = res
+        if verbose:
             print("Elapsed time (only wavelet convolution): {} seconds to analyze {} frequencies".format(
                 _time.time() - start_time, frequencies.size))
-        self._multichannel = bool(multichannel)
-        self._result = out
-        self._host = None
-        if not keep_on_device:
-            self._materialise()
-            self._result = None
 
     # ------------------------------------------------------------------ results
     def _materialise(self):

@@ -109,13 +109,32 @@ int gcwt_execute(gcwt_plan *plan, const void *x, int32_t in_type,
                  void *out, int64_t out_scale_stride, int64_t out_channel_stride,
                  void *stream);
 
-/* Same, with HOST pointers (no halos): allocates device buffers, copies in, runs,
- * copies out, synchronises.  The call a ctypes/cgo-style binding makes when the caller
- * has no device memory of its own. */
+/* The whole transform body for HOST buffers: what transform() does between `input_asarray -= mean`
+ * and `self._amplitude = out_array` (ghost/wave/transforms.py:142-143, 185, 202-204, 231).
+ *
+ *   x             host pointer, n_channels rows of n_samples (x_stride elements apart); never written
+ *   epoch_bounds  n_epochs pairs [start, stop) of sample indices, ascending; every epoch is convolved on
+ *                 its own with zero padding (transforms.py:202-204) and samples outside all epochs are
+ *                 zero in the result.  NULL / 0: one epoch [0, n_samples)
+ *   means_host    one double per channel, or NULL for each channel's mean over all n_samples
+ *                 (transforms.py:143 subtracts the mean of the WHOLE array, not of an epoch)
+ *   out           host pointer, coefficient (c, s, t) at out[c * out_channel_stride + s * out_scale_stride + t]
+ *
+ * The result is streamed: tiles of (channel group x scales x time stretch) alternate between two
+ * plan-owned device buffers and travel to the host while the next tile is computed, so results larger
+ * than device memory work and device memory holds one channel group's samples plus two tiles.  A pinned
+ * `out` (cudaHostAlloc, cudaHostRegister, torch pin_memory) is written by DMA directly; a pageable one is
+ * filled from a plan-owned pinned ring by a few host threads.  Synchronous: returns when `out` is complete.
+ * One call at a time per plan. */
 int gcwt_execute_host(gcwt_plan *plan, const void *x, int32_t in_type,
                       int64_t n_channels, int64_t n_samples, int64_t x_stride,
+                      const int64_t *epoch_bounds, int32_t n_epochs,
                       const double *means_host,
                       void *out, int64_t out_scale_stride, int64_t out_channel_stride);
+
+/* Diagnostics of the last gcwt_execute_host: out4 = {wall ms, 1 if `out` was pinned (direct DMA) else 0,
+ * tiles, bytes copied to the host}. */
+int gcwt_host_stats(const gcwt_plan *plan, double *out4);
 
 /* Per-channel mean in float64 (transforms.py:143): means[c] = mean(x[c, 0:n_samples]). */
 int gcwt_channel_means(const void *x, int32_t in_type, int64_t n_channels,

@@ -7,7 +7,7 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 bdir=$root/ghost_b200/variants/build_$tag
 mkdir -p "$bdir"
 cd "$root/ghost_b200/csrc"
-for f in cabi generic_path fast_path sigtools; do
+for f in cabi generic_path fast_path sigtools host_path; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O3 $flags -c $f.cu -o "$bdir/$f.o" &
 done
 wait
