@@ -19,7 +19,8 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = ["channel_block", "time_block", "global_means", "exchange_halos", "run_channel_shard",
-           "run_time_shard", "run_time_shard_tiled", "required_halo"]
+           "run_time_shard", "run_time_shard_tiled", "required_halo", "HaloExchange", "check_time_shards",
+           "gather_shard_lengths"]
 
 
 def _dist():
@@ -61,50 +62,82 @@ def global_means(local_sum, local_count, group=None):
     return buf[:-1] / buf[-1]
 
 
-def exchange_halos(core, halo, rank, world, group=None):
-    """Return ``(padded, halo_left, halo_right)``: ``core`` (channels, n_local) extended by
-    up to ``halo`` samples from rank-1 on the left and rank+1 on the right.
-
-    A neighbour shorter than ``halo`` contributes what it has (the caller should size
-    shards so that they are longer than the halo).  Rank 0 / world-1 get no halo on their
-    outer side: the true signal edges are zero-padded by the kernels, like the reference.
-    """
+def gather_shard_lengths(n_local, rank, world, device, group=None):
+    """Every rank's shard length (one all-gather of an int64)."""
     import torch
     dist = _dist()
-    n_ch, n_local = core.shape
-    lens = [torch.zeros(1, dtype=torch.int64, device=core.device) for _ in range(world)]
-    mine = torch.tensor([n_local], dtype=torch.int64, device=core.device)
+    mine = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
     if world > 1:
+        lens = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
         dist.all_gather(lens, mine, group=group)
     else:
         lens = [mine]
-    lens = [int(v.item()) for v in lens]
-    hl = min(halo, lens[rank - 1]) if rank > 0 else 0
-    hr = min(halo, lens[rank + 1]) if rank < world - 1 else 0
-    padded = torch.empty((n_ch, hl + n_local + hr), dtype=core.dtype, device=core.device)
-    padded[:, hl:hl + n_local] = core
-    ops = []
-    send_r = send_l = recv_l = recv_r = None
-    if rank < world - 1:                                  # my tail is the right neighbour's left halo
-        k = min(halo, n_local)
-        send_r = core[:, n_local - k:].contiguous()
-        ops.append(dist.P2POp(dist.isend, send_r, rank + 1, group))
-        recv_r = torch.empty((n_ch, hr), dtype=core.dtype, device=core.device)
-        ops.append(dist.P2POp(dist.irecv, recv_r, rank + 1, group))
-    if rank > 0:
-        k = min(halo, n_local)
-        send_l = core[:, :k].contiguous()
-        ops.append(dist.P2POp(dist.isend, send_l, rank - 1, group))
-        recv_l = torch.empty((n_ch, hl), dtype=core.dtype, device=core.device)
-        ops.append(dist.P2POp(dist.irecv, recv_l, rank - 1, group))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
+    return [int(v.item()) for v in lens]
+
+
+def check_time_shards(lens, halo):
+    """Raise -- on every rank alike, since all ranks hold the same ``lens`` -- when the partition cannot
+    be transformed exactly: an empty shard would leave a rank without work (and the others waiting in
+    the collectives), and a shard shorter than ``halo`` next to an interior seam cannot supply its
+    neighbour's halo (the samples of rank +-2 would silently read as zero padding)."""
+    for r, n in enumerate(lens):
+        if n <= 0:
+            raise ValueError("time shard of rank {} is empty ({} ranks for these samples): use fewer ranks"
+                             " or a smaller alignment".format(r, len(lens)))
+    for r in range(len(lens) - 1):
+        if lens[r] < halo or lens[r + 1] < halo:
+            raise ValueError("time shards of ranks {} and {} hold {} and {} samples but each must supply a halo"
+                             " of {} samples (the widest wavelet's support): use fewer ranks".format(
+                                 r, r + 1, lens[r], lens[r + 1], halo))
+
+
+class HaloExchange:
+    """The halo send / receive pairs with both neighbours, posted at construction and completed by
+    ``wait()`` -- so that the tiles which need no neighbour data can be transformed in between.
+
+    ``left`` / ``right`` (after ``wait``): (channels, halo) tensors holding the last ``halo`` samples of
+    rank - 1 and the first ``halo`` samples of rank + 1, or None at the true ends of the recording
+    (which the kernels zero-pad, like the reference)."""
+
+    def __init__(self, core, halo, rank, world, group=None):
+        import torch
+        dist = _dist()
+        n_ch, n_local = core.shape
+        self.left = self.right = None
+        self._reqs = []
+        self._keep = []
+        ops = []
+        if halo > 0 and rank < world - 1:
+            tail = core[:, n_local - halo:].contiguous()
+            self.right = torch.empty((n_ch, halo), dtype=core.dtype, device=core.device)
+            ops += [dist.P2POp(dist.isend, tail, rank + 1, group), dist.P2POp(dist.irecv, self.right, rank + 1, group)]
+            self._keep.append(tail)
+        if halo > 0 and rank > 0:
+            head = core[:, :halo].contiguous()
+            self.left = torch.empty((n_ch, halo), dtype=core.dtype, device=core.device)
+            ops += [dist.P2POp(dist.isend, head, rank - 1, group), dist.P2POp(dist.irecv, self.left, rank - 1, group)]
+            self._keep.append(head)
+        if ops:
+            self._reqs = dist.batch_isend_irecv(ops)
+
+    def wait(self):
+        for req in self._reqs:
             req.wait()
-    if recv_l is not None:
-        padded[:, :hl] = recv_l
-    if recv_r is not None:
-        padded[:, hl + n_local:] = recv_r
-    return padded, hl, hr
+        self._reqs = []
+        return self.left, self.right
+
+
+def exchange_halos(core, halo, rank, world, group=None):
+    """Return ``(padded, halo_left, halo_right)``: ``core`` (channels, n_local) extended by ``halo``
+    samples from rank-1 on the left and rank+1 on the right (blocking form; the transform paths below use
+    :class:`HaloExchange` and never copy the whole shard).  Raises on every rank when a shard is empty or
+    shorter than ``halo`` (:func:`check_time_shards`)."""
+    import torch
+    lens = gather_shard_lengths(core.shape[1], rank, world, core.device, group)
+    check_time_shards(lens, halo)
+    left, right = HaloExchange(core, halo, rank, world, group).wait()
+    parts = ([left] if left is not None else []) + [core] + ([right] if right is not None else [])
+    return torch.cat(parts, dim=1), (0 if left is None else halo), (0 if right is None else halo)
 
 
 def run_channel_shard(plan, x_local, out=None):
@@ -112,44 +145,91 @@ def run_channel_shard(plan, x_local, out=None):
     return plan.execute(x_local, out)
 
 
-def run_time_shard(plan, core, rank, world, out=None, group=None):
+def _time_shard_tiles(plan, core, rank, world, tile, emit, group=None, means=None):
+    """Shared driver of the time-sharded transforms.  ``emit(a, b)`` returns ``(out, out_start)`` for the
+    tile of core samples [a, b) and is told when the tile is complete through ``emit.done(out, a, b)``.
+
+    Collectives: one all-reduce (global mean, reference transforms.py:143), one all-gather of shard
+    lengths, one batched send/recv of ``L_max - 1`` samples with each neighbour.  The exchange is posted
+    first; the interior tiles -- every tile further than the halo from both ends of the shard -- are
+    transformed while it is in flight; the tiles next to a seam follow from small edge buffers
+    (halo + tile samples), so the shard itself is never copied."""
+    import torch
+    n_ch, n_local = core.shape
+    halo = required_halo(plan)
+    # lengths first: an unusable partition must raise on every rank before any rank enters another collective
+    lens = gather_shard_lengths(n_local, rank, world, core.device, group)
+    check_time_shards(lens, halo)
+    if means is None:
+        sums = plan.channel_means(core) * float(n_local)
+        means = global_means(sums, n_local, group)
+    xch = HaloExchange(core, halo, rank, world, group)
+    has_l, has_r = rank > 0 and halo > 0, rank < world - 1 and halo > 0
+    tile = int(min(tile, n_local))
+    tiles = [(a, min(n_local, a + tile)) for a in range(0, n_local, tile)]
+    edge = []
+    done = 0
+    for a, b in tiles:
+        if (has_l and a < halo) or (has_r and n_local - b < halo):
+            edge.append((a, b))
+            continue
+        out, o0 = emit(a, b)
+        plan.execute(core, out, means=means, start=a, stop=b, halo_left=min(halo, a), halo_right=min(halo, n_local - b),
+                     out_start=o0)
+        emit.done(out, a, b)
+        done += (b - a) * n_ch * plan.n_scales
+    left, right = xch.wait()
+    for a, b in edge:
+        # [left halo | core[lo:hi] | right halo]: only as much of the core as this tile can reach
+        lo, hi = max(0, a - halo), min(n_local, b + halo)
+        parts, off = [], 0
+        if has_l and a < halo:
+            parts.append(left[:, a:])                      # the last (halo - a) samples of rank - 1
+            off = halo - a
+        parts.append(core[:, lo:hi])
+        hr = 0
+        if has_r and n_local - b < halo:
+            hr = halo - (n_local - b)
+            parts.append(right[:, :hr])
+        buf = torch.cat(parts, dim=1)
+        start = off + (a - lo)
+        out, o0 = emit(a, b)
+        plan.execute(buf, out, means=means, start=start, stop=start + (b - a), halo_left=min(halo, start),
+                     halo_right=min(halo, buf.shape[1] - (start + (b - a))), out_start=o0)
+        emit.done(out, a, b)
+        done += (b - a) * n_ch * plan.n_scales
+    return done
+
+
+class _Emit:
+    def __init__(self, get, done=None):
+        self._get, self._done = get, done
+
+    def __call__(self, a, b):
+        return self._get(a, b)
+
+    def done(self, out, a, b):
+        if self._done is not None:
+            self._done(out, a, b)
+
+
+def run_time_shard(plan, core, rank, world, out=None, group=None, tile=None):
     """Time-sharded transform of this rank's ``core`` (channels, n_local) CUDA tensor.
 
-    Returns the (channels, scales, n_local) coefficients of the core samples.  Collectives:
-    one all-reduce (global mean), one all-gather of shard lengths, one batched send/recv
-    of halos with the two neighbours.
-    """
-    import torch
+    Returns the (channels, scales, n_local) coefficients of the core samples (they stay sharded)."""
     n_local = core.shape[1]
-    sums = plan.channel_means(core) * float(n_local)
-    means = global_means(sums, n_local, group)
-    padded, hl, hr = exchange_halos(core, required_halo(plan), rank, world, group)
     if out is None:
         out = plan.alloc_out(core.shape[0], n_local)
-    plan.execute(padded, out, means=means, start=hl, stop=hl + n_local, halo_left=hl, halo_right=hr,
-                 out_start=0)
+    _time_shard_tiles(plan, core, rank, world, n_local if tile is None else tile, _Emit(lambda a, b: (out, a)), group)
     return out
 
 
-def run_time_shard_tiled(plan, core, rank, world, tile, out=None, consumer=None, group=None):
-    """As :func:`run_time_shard` for shards whose coefficients do not fit in device memory: after
-    the mean all-reduce and the halo exchange the shard is transformed in time tiles into a
-    reused (channels, scales, tile) buffer (see ``CwtPlan.execute_tiled``).  Returns the number
-    of coefficients produced on this rank."""
-    n_local = core.shape[1]
-    sums = plan.channel_means(core) * float(n_local)
-    means = global_means(sums, n_local, group)
-    padded, hl, hr = exchange_halos(core, required_halo(plan), rank, world, group)
-    tile = int(min(tile, n_local))
+def run_time_shard_tiled(plan, core, rank, world, tile, out=None, consumer=None, group=None, means=None):
+    """As :func:`run_time_shard` for shards whose coefficients do not fit in device memory: the shard is
+    transformed in time tiles into a reused (channels, scales, tile) buffer and every finished tile is
+    handed to ``consumer(out, a, b)`` (core sample range [a, b); interior tiles come first, the tiles
+    next to a seam last).  Returns the number of coefficients produced on this rank."""
+    tile = int(min(tile, core.shape[1]))
     if out is None:
         out = plan.alloc_out(core.shape[0], tile)
-    halo = required_halo(plan)
-    done = 0
-    for a in range(0, n_local, tile):
-        b = min(n_local, a + tile)
-        plan.execute(padded, out, means=means, start=hl + a, stop=hl + b,
-                     halo_left=min(halo, hl + a), halo_right=min(halo, n_local - b + hr), out_start=0)
-        if consumer is not None:
-            consumer(out, a, b)
-        done += (b - a) * core.shape[0] * plan.n_scales
-    return done
+    return _time_shard_tiles(plan, core, rank, world, tile, _Emit(lambda a, b: (out, 0), consumer), group, means)

@@ -92,6 +92,7 @@ class ContinuousWaveletTransform(WaveletTransform):
         self._result = None          # torch tensor (C, S, N) on the device, or None
         self._host = None            # numpy view of the result, filled lazily
         self._multichannel = False
+        self._time_auto = None       # (n, fs) when self._time is the implicit arange(n) / fs
         self._plans = {}
         self.last_plan = None
 
@@ -170,12 +171,19 @@ class ContinuousWaveletTransform(WaveletTransform):
                     raise TypeError("multichannel input must be a (channels, samples) ndarray")
                 if fs is None:
                     raise TypeError("transform() missing 1 required keyword argument: 'fs'")
-                _, fs, timestamps, epoch_bounds = standardize_input(
-                    data[0], fs=fs, timestamps=timestamps, n_signals=1)
+                if timestamps is None and self._time_auto == (data.shape[1], fs):
+                    # same implicit time base as the previous call (batches of channels of one recording)
+                    timestamps, epoch_bounds = self._time, np.array([[0, data.shape[1]]], dtype=int)
+                else:
+                    auto = timestamps is None
+                    _, fs, timestamps, epoch_bounds = standardize_input(
+                        data[0], fs=fs, timestamps=timestamps, n_signals=1)
+                    self._time_auto = (data.shape[1], fs) if auto else None
                 x_host = data
         else:
             samples, fs, timestamps, epoch_bounds = standardize_input(
                 data, fs=fs, timestamps=timestamps, n_signals=1)
+            self._time_auto = None
             x_host = samples.squeeze()[None, :]
 
         self.fs = fs                       # validates (transforms.py:109, :457-462)

@@ -111,3 +111,77 @@ def test_partition_helpers():
     blocks = [sharding.time_block(2592000000, r, 8, align=16384) for r in range(8)]
     assert blocks[0][0] == 0 and blocks[-1][1] == 2592000000
     assert all(a[1] == b[0] and a[1] % 16384 == 0 for a, b in zip(blocks[:-1], blocks[1:]))
+
+
+def _worker_tiled(rank, world, port, n, ntaps, tile, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        x = rng.standard_normal((2, n)) - 1.0
+        taps = rng.standard_normal(ntaps) + 1j * rng.standard_normal(ntaps)
+        plan = FakePlan(taps)
+        lo, hi = sharding.time_block(n, rank, world, align=8)
+        core = torch.from_numpy(x[:, lo:hi].copy())
+        got = torch.zeros((2, 1, hi - lo), dtype=torch.complex128)
+        order = []
+
+        def consumer(out, a, b):
+            got[:, :, a:b] = out[:, :, :b - a]
+            order.append((a, b))
+
+        done = sharding.run_time_shard_tiled(plan, core, rank, world, tile, consumer=consumer)
+        whole = FakePlan(taps).execute(torch.from_numpy(x), plan.alloc_out(2, n), means=torch.from_numpy(x.mean(axis=1)),
+                                       start=0, stop=n, halo_left=0, halo_right=0)
+        ret[rank] = (float((got - whole[:, :, lo:hi]).abs().max()), done, hi - lo, order)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,ntaps,tile", [(2, 6000, 301, 500), (3, 9000, 257, 1000), (2, 4000, 129, 4000)])
+def test_time_shard_tiles_overlap_the_exchange(world, n, ntaps, tile):
+    """Tiled time shards: interior tiles are transformed while the halos travel, the tiles next to a seam
+    afterwards from small edge buffers; the union equals the unsharded transform."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_tiled, args=(world, port, n, ntaps, tile, ret), nprocs=world, join=True)
+    for r in range(world):
+        err, done, n_local, order = ret[r]
+        assert err < 1e-9, (r, err)
+        assert done == 2 * n_local
+        assert sorted(order) == [(a, min(n_local, a + tile)) for a in range(0, n_local, tile)]
+        if tile < n_local and world > 1:
+            seam_tiles = [t for t in order if (r > 0 and t[0] < ntaps - 1) or (r < world - 1 and n_local - t[1] < ntaps - 1)]
+            assert order[-len(seam_tiles):] == seam_tiles            # the tiles that need neighbour data come last
+
+
+def _worker_bad(rank, world, port, n, ntaps, align, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = np.random.default_rng(1).standard_normal((1, n))
+        plan = FakePlan(np.ones(ntaps, dtype=complex))
+        lo, hi = sharding.time_block(n, rank, world, align=align)
+        core = torch.from_numpy(x[:, lo:hi].copy())
+        try:
+            sharding.run_time_shard(plan, core, rank, world)      # also on a rank whose shard is empty
+            ret[rank] = "no error"
+        except ValueError as e:
+            ret[rank] = str(e)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,ntaps,align,needle", [(1000, 801, 1, "must supply a halo"), (1000, 31, 512, "is empty")])
+def test_time_shards_too_short_or_empty_raise_on_every_rank(n, ntaps, align, needle):
+    """a shard shorter than the halo (or empty) must not be transformed with silent zero
+    padding (or hang the collectives): every rank raises the same ValueError."""
+    world = 3 if needle == "is empty" else 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_bad, args=(world, port, n, ntaps, align, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert needle in ret[r], (r, ret[r])
