@@ -184,6 +184,9 @@ int gcwt_plan_destroy(gcwt_plan* p) {
     if (p->d_means) cudaFree(p->d_means);
     if (p->d_partial) cudaFree(p->d_partial);
     if (p->d_twiddle) cudaFree(p->d_twiddle);
+    if (p->d_tw1k) cudaFree(p->d_tw1k);
+    if (p->d_tw_fine) cudaFree(p->d_tw_fine);
+    if (p->d_hcache) cudaFree(p->d_hcache);
     for (int k = 0; k < gcwt_plan::kSideStreams; ++k) {
         if (p->side_stream[k]) { cudaStreamSynchronize(p->side_stream[k]); cudaStreamDestroy(p->side_stream[k]); }
         if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]);

@@ -9,7 +9,10 @@
 #include "common.cuh"
 #include "multiplier.cuh"
 #include "fft_global.cuh"
+#include "fft_fourstep.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 namespace gcwt {
 
@@ -102,14 +105,16 @@ __global__ void generic_load_kernel(const TIn* __restrict__ x, int64_t x_stride,
 
 // ----------------------------------------------------------------------------- response
 // H_s on the n-point grid, scaled by 1/n.  Kernel (2)'s multiplier, evaluated in registers.
+// p2 >= 0: position j holds bin k1 + 2^p1 * k2 with k1 = j >> p2, k2 = j & (2^p2 - 1) (four-step order)
 template <typename T>
 __global__ void generic_response_kernel(const ScaleInfo* __restrict__ scales,
                                         const double* __restrict__ terms,
                                         const int* __restrict__ ids, int nfft,
-                                        typename cplx_of<T>::type* __restrict__ H) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nfft) return;
-    const ScaleInfo sc = scales[ids[blockIdx.y]];
+                                        typename cplx_of<T>::type* __restrict__ H, int p1 = -1, int p2 = -1) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= nfft) return;
+    const int j = p2 < 0 ? pos : (pos >> p2) + ((pos & ((1 << p2) - 1)) << p1);
+    const ScaleInfo sc = scales[ids ? ids[blockIdx.y] : (int)blockIdx.y];
     double g = morse_response(j, nfft, sc.L, sc.k_first, sc.n_terms, terms + sc.term_off);
     g /= (double)nfft;
     double re = g, im = 0.0;
@@ -119,7 +124,7 @@ __global__ void generic_response_kernel(const ScaleInfo* __restrict__ scales,
         re = g * c;
         im = g * s;
     }
-    H[(int64_t)blockIdx.y * nfft + j] = mk<T>((T)re, (T)im);
+    H[(int64_t)blockIdx.y * nfft + pos] = mk<T>((T)re, (T)im);
 }
 
 template <typename T>
@@ -154,6 +159,121 @@ __global__ void generic_epilogue_kernel(const typename cplx_of<T>::type* __restr
     else ((TOut*)out)[o] = (TOut)(v.x * v.x + v.y * v.y);
 }
 
+// ----------------------------------------------------------------------------- four-step driver (fp64)
+template <typename TOut>
+static void launch_fs_cols(int kind, dim3 grid, cudaStream_t st, const FourStepParams& fp, const double2* T, int sb,
+                           const int* ids, void* out, int64_t s_stride, int64_t c_stride) {
+    static bool attr[3] = {false, false, false};
+    auto set = [&](auto kern, int k) {
+        if (!attr[k]) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFourStepSmem); attr[k] = true; }
+    };
+    if (kind == GCWT_OUT_COMPLEX) {
+        set(fs_inverse_cols_kernel<TOut, GCWT_OUT_COMPLEX>, 0);
+        fs_inverse_cols_kernel<TOut, GCWT_OUT_COMPLEX><<<grid, 256, kFourStepSmem, st>>>(fp, T, sb, ids, out, s_stride, c_stride);
+    } else if (kind == GCWT_OUT_AMPLITUDE) {
+        set(fs_inverse_cols_kernel<TOut, GCWT_OUT_AMPLITUDE>, 1);
+        fs_inverse_cols_kernel<TOut, GCWT_OUT_AMPLITUDE><<<grid, 256, kFourStepSmem, st>>>(fp, T, sb, ids, out, s_stride, c_stride);
+    } else {
+        set(fs_inverse_cols_kernel<TOut, GCWT_OUT_POWER>, 2);
+        fs_inverse_cols_kernel<TOut, GCWT_OUT_POWER><<<grid, 256, kFourStepSmem, st>>>(fp, T, sb, ids, out, s_stride, c_stride);
+    }
+}
+
+template <typename TIn, typename TOut>
+static int generic_run_fourstep(gcwt_plan* p, const std::vector<int>& ids, const TIn* x, int64_t n_channels, int64_t n,
+                                int64_t x_stride, int64_t halo_l, int64_t halo_r, const double* d_means, void* out,
+                                int64_t s_stride, int64_t c_stride, cudaStream_t st, int64_t nfft, int64_t lmax) {
+    const int ns = (int)ids.size();
+    const FourStep fs(nfft);
+    const int64_t offset = lmax / 2, hop = nfft - (lmax - 1);
+    const int64_t n_chunks = (n + hop - 1) / hop, n_items = n_channels * n_chunks;
+    static bool attr_done = false;
+    if (!attr_done) {
+        GCWT_CUDA_OK(cudaFuncSetAttribute(fs_forward_cols_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFourStepSmem));
+        GCWT_CUDA_OK(cudaFuncSetAttribute(fs_forward_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFourStepSmem));
+        GCWT_CUDA_OK(cudaFuncSetAttribute(fs_inverse_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFourStepSmem));
+        attr_done = true;
+    }
+    // ---- tables ------------------------------------------------------------------------------
+    if (!p->d_tw1k) {
+        std::vector<double2> tw(1024);
+        for (int j = 0; j < 1024; ++j) {
+            // exact octant symmetry is not needed: fp64 sin / cos of an exactly representable multiple of pi / 512
+            tw[j] = make_double2(std::cos(-2.0 * M_PI * j / 1024.0), std::sin(-2.0 * M_PI * j / 1024.0));
+        }
+        GCWT_CUDA_OK(cudaMalloc((void**)&p->d_tw1k, sizeof(double2) * 1024));
+        GCWT_CUDA_OK(cudaMemcpyAsync(p->d_tw1k, tw.data(), sizeof(double2) * 1024, cudaMemcpyHostToDevice, st));
+        GCWT_CUDA_OK(cudaStreamSynchronize(st));
+        GCWT_CUDA_OK(cudaMalloc((void**)&p->d_tw_fine, sizeof(double2) * 1024));
+    }
+    if (p->tw_fine_n != nfft) {
+        fs_fine_twiddle_kernel<<<4, 256, 0, st>>>(fs.p, p->d_tw_fine);
+        count_launch();
+        p->tw_fine_n = nfft;
+    }
+    // ---- batch geometry --------------------------------------------------------------------------
+    const size_t row = (size_t)nfft * sizeof(double2);
+    // intermediate of one launch pair.  Measured on config 5: 32 ... 96 MB (L2-sized) 21.3 ms, 192 MB 19.9, 512 MB 19.3 --
+    // the kernels are bound by shared-memory wavefronts, not by HBM, so fewer and larger launches win
+    size_t t_budget = (size_t)512 << 20;
+    if (const char* e = getenv("GCWT_F64_TBATCH_MB")) t_budget = (size_t)std::max(1, atoi(e)) << 20;
+    const int ib = (int)std::max<int64_t>(1, std::min<int64_t>(n_items, (int64_t)(((size_t)256 << 20) / row)));
+    const int sb = (int)std::max<int64_t>(1, std::min<int64_t>(ns, (int64_t)(t_budget / (row * ib))));
+    // the responses of a whole plan are cached when they fit (they depend on the scale and nfft only)
+    bool contiguous = true;
+    for (int i = 1; i < ns; ++i) contiguous = contiguous && ids[i] == ids[i - 1] + 1;
+    const bool cache = contiguous && ns == p->n_scales && (size_t)p->n_scales * row <= ((size_t)4 << 30);
+    if (cache && p->hcache_n != nfft) {
+        if (p->d_hcache) { GCWT_CUDA_OK(cudaStreamSynchronize(st)); cudaFree(p->d_hcache); p->d_hcache = nullptr; p->hcache_n = 0; }
+        if (cudaMalloc((void**)&p->d_hcache, (size_t)p->n_scales * row) == cudaSuccess) {
+            generic_response_kernel<double><<<dim3((unsigned)((nfft + 255) / 256), p->n_scales), 256, 0, st>>>(
+                p->d_scales, p->d_terms, nullptr, (int)nfft, p->d_hcache, fs.p1, fs.p2);
+            count_launch();
+            p->hcache_n = nfft;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    const bool cached = cache && p->hcache_n == nfft;
+    // layout: U[ib] | Y[ib] | T[ib*sb] | H[sb] (unless cached) | ids[ns]
+    const size_t need = row * ((size_t)2 * ib + (size_t)ib * sb + (cached ? 0 : sb)) + sizeof(int) * ns + 256;
+    int rc = ensure_workspace(p, need);
+    if (rc) return rc;
+    char* w = (char*)p->ws.ptr;
+    double2* U = (double2*)w;      w += row * ib;
+    double2* Y = (double2*)w;      w += row * ib;
+    double2* T = (double2*)w;      w += row * (size_t)ib * sb;
+    double2* Hb = (double2*)w;     if (!cached) w += row * sb;
+    int* d_ids = (int*)w;
+    GCWT_CUDA_OK(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+
+    FourStepParams fp;
+    fp.p = fs.p; fp.p1 = fs.p1; fp.p2 = fs.p2; fp.tw = p->d_tw1k; fp.tw_fine = p->d_tw_fine;
+    fp.n_chunks = n_chunks; fp.hop = hop; fp.offset = offset; fp.n = n; fp.halo_l = halo_l; fp.halo_r = halo_r;
+    const unsigned col_blocks = (unsigned)(fs.n2 / fs.cols_per_block), row_blocks = (unsigned)(fs.n1 / fs.rows_per_block);
+    for (int64_t i0 = 0; i0 < n_items; i0 += ib) {
+        const int ibn = (int)std::min<int64_t>(ib, n_items - i0);
+        fp.item0 = i0; fp.n_items = ibn;
+        fs_forward_cols_kernel<TIn><<<col_blocks * ibn, 256, kFourStepSmem, st>>>(fp, x, x_stride, d_means, U);
+        fs_forward_rows_kernel<<<row_blocks * ibn, 256, kFourStepSmem, st>>>(fp, U, Y);
+        count_launch(2);
+        for (int s0 = 0; s0 < ns; s0 += sb) {
+            const int sbn = std::min(sb, ns - s0);
+            const double2* H = cached ? p->d_hcache + ((int64_t)ids[s0] << fs.p) : Hb;
+            if (!cached) {
+                generic_response_kernel<double><<<dim3((unsigned)((nfft + 255) / 256), sbn), 256, 0, st>>>(
+                    p->d_scales, p->d_terms, d_ids + s0, (int)nfft, Hb, fs.p1, fs.p2);
+                count_launch();
+            }
+            fs_inverse_rows_kernel<<<dim3(row_blocks * ibn, sbn), 256, kFourStepSmem, st>>>(fp, Y, H, T, sbn);
+            launch_fs_cols<TOut>(p->out_kind, dim3(col_blocks * ibn, sbn), st, fp, T, sbn, d_ids + s0, out, s_stride, c_stride);
+            count_launch(2);
+        }
+    }
+    GCWT_CUDA_OK(cudaGetLastError());
+    return GCWT_OK;
+}
+
 // ----------------------------------------------------------------------------- driver
 template <typename TIn, typename T, typename TOut>
 static int generic_run(gcwt_plan* p, const std::vector<int>& ids, const TIn* x, int64_t n_channels,
@@ -170,6 +290,9 @@ static int generic_run(gcwt_plan* p, const std::vector<int>& ids, const TIn* x, 
     else nfft = std::max<int64_t>(int64_t(1) << 17, int64_t(1) << ilog2_ceil(4 * lmax));
     if (nfft > (int64_t(1) << 26)) { set_error("generic path: kernel too long"); return GCWT_ERR_UNSUPPORTED; }
     if (nfft < 16) nfft = 16;
+    if (std::is_same<T, double>::value && FourStep::usable(nfft) && !getenv("GCWT_F64_LEGACY"))
+        return generic_run_fourstep<TIn, TOut>(p, ids, x, n_channels, n, x_stride, halo_l, halo_r, d_means, out, s_stride,
+                                               c_stride, st, nfft, lmax);
     const int64_t offset = lmax / 2;
     const int64_t hop = nfft - (lmax - 1);
     const int64_t n_chunks = (n + hop - 1) / hop;

@@ -130,6 +130,12 @@ struct gcwt_plan {
     int64_t guard_last = 0, guard_total = 0, guard_checked = 0;   // re-computed (channel, scale) pairs
     std::vector<unsigned char> guard_last_flags;                  // any-channel flag per scale of the last call
     std::vector<float> guard_gain_h, guard_q_h;                   // host copies of the tables (diagnostics)
+    // fp64 four-step path: twiddle tables and the cache of filter responses (transposed order) for one nfft
+    double2* d_tw1k = nullptr;              // e^{-2 pi i j / 1024}
+    double2* d_tw_fine = nullptr;           // e^{-2 pi i j / nfft}, j < 1024
+    int64_t tw_fine_n = 0;
+    double2* d_hcache = nullptr;            // [n_scales][nfft]
+    int64_t hcache_n = 0;
     // host-buffer path (gcwt_execute_host): persistent staging, grown on demand
     struct HostStage {
         void* d_in = nullptr; size_t in_bytes = 0;           // the channel group's samples
