@@ -17,6 +17,7 @@ OUT_COMPLEX, OUT_AMPLITUDE, OUT_POWER = 0, 1, 2
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_INTERP = 2
 FLAG_NO_GUARD = 4
+POOL_MEAN, POOL_MAX = 0, 1
 
 EXPORTS = (
     "gcwt_version", "gcwt_last_error", "gcwt_launch_count", "gcwt_plan_create",
@@ -24,7 +25,7 @@ EXPORTS = (
     "gcwt_channel_means", "gcwt_execute", "gcwt_execute_host", "gcwt_filter_response",
     "gcwt_morse_kernel", "gcwt_profile_enable", "gcwt_profile_read",
     "gcwt_fastconv", "gcwt_dft", "gcwt_analytic_signal", "gcwt_moments", "gcwt_interp_taps",
-    "gcwt_guard_stats", "gcwt_host_stats",
+    "gcwt_guard_stats", "gcwt_host_stats", "gcwt_pool_rows", "gcwt_execute_host_pooled",
 )
 
 
@@ -75,6 +76,8 @@ def load():
     lib.gcwt_execute.argtypes = [vp, vp, i32, i64, i64, i64, i64, i64, vp, vp, i64, i64, vp]
     lib.gcwt_execute_host.argtypes = [vp, vp, i32, i64, i64, i64, vp, i32, vp, vp, i64, i64]
     lib.gcwt_host_stats.argtypes = [vp, dp]
+    lib.gcwt_pool_rows.argtypes = [vp, i32, i64, i64, i64, i64, i32, i32, vp, i64, i32, vp]
+    lib.gcwt_execute_host_pooled.argtypes = [vp, vp, i32, i64, i64, i64, vp, i64, i32, vp, i64, i64]
     lib.gcwt_filter_response.argtypes = [i64, i32, i32, dp, i64, i64, i64, dp, i32]
     lib.gcwt_morse_kernel.argtypes = [i64, i32, i32, dp, dp, i32]
     lib.gcwt_fastconv.argtypes = [dp, i32, i64, dp, i32, i64, dp, i32]

@@ -318,6 +318,28 @@ int gcwt_execute_host(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_ch
                         out_scale_stride, out_channel_stride, tile_hint);
 }
 
+int gcwt_execute_host_pooled(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_channels, int64_t n_samples,
+                             int64_t x_stride, const double* means_host, int64_t pool_width, int32_t pool_mode,
+                             double* out, int64_t out_scale_stride, int64_t out_channel_stride) {
+    int rc = check_exec_args(p, x, in_type, n_channels, n_samples, x_stride, out);
+    if (rc) return rc;
+    if (pool_width < 1 || (pool_mode != GCWT_POOL_MEAN && pool_mode != GCWT_POOL_MAX)) { set_error("execute_host_pooled: bad pool_width / pool_mode"); return GCWT_ERR_ARG; }
+    if (out_scale_stride < (n_samples + pool_width - 1) / pool_width) { set_error("execute_host_pooled: out_scale_stride smaller than the bin count"); return GCWT_ERR_ARG; }
+    GCWT_CUDA_OK(cudaSetDevice(p->device));
+    int64_t tile_hint = 0;
+    if (const char* e = getenv("GCWT_HOST_TILE")) tile_hint = atoll(e);
+    return host_execute(p, x, in_type, n_channels, n_samples, x_stride, nullptr, 0, means_host, out, out_scale_stride,
+                        out_channel_stride, tile_hint, pool_width, pool_mode);
+}
+
+int gcwt_pool_rows(const void* x_dev, int32_t type, int64_t n_rows, int64_t n_cols, int64_t row_stride, int64_t pool_width,
+                   int32_t pool_mode, int32_t square, double* out_dev, int64_t out_stride, int32_t device, void* stream) {
+    if (!x_dev || !out_dev || (type != GCWT_F32 && type != GCWT_F64)) { set_error("pool_rows: bad argument"); return GCWT_ERR_ARG; }
+    GCWT_CUDA_OK(cudaSetDevice(device));
+    return pool_rows_launch(x_dev, type, n_rows, n_cols, row_stride, pool_width, pool_mode, square, out_dev, out_stride,
+                            (cudaStream_t)stream);
+}
+
 int gcwt_host_stats(const gcwt_plan* p, double* out4) {
     if (!p || !out4) { set_error("host_stats: NULL argument"); return GCWT_ERR_ARG; }
     for (int k = 0; k < 4; ++k) out4[k] = p->host.last_ms[k];

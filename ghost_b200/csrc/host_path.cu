@@ -46,6 +46,8 @@ void host_stage_free(gcwt_plan* p) {
     for (int b = 0; b < 2; ++b) {
         if (h.d_out[b]) cudaFree(h.d_out[b]);
         if (h.h_ring[b]) cudaFreeHost(h.h_ring[b]);
+        if (h.d_pool[b]) cudaFree(h.d_pool[b]);
+        if (h.h_pool[b]) cudaFreeHost(h.h_pool[b]);
         if (h.ev_done[b]) cudaEventDestroy(h.ev_done[b]);
         if (h.ev_out[b]) cudaEventDestroy(h.ev_out[b]);
     }
@@ -86,7 +88,9 @@ static void copy_rows(const RowCopy& rc, int n_threads) {
 
 int host_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, int64_t n, int64_t x_stride,
                  const int64_t* epochs, int n_epochs, const double* means_host, void* out, int64_t s_stride,
-                 int64_t c_stride, int64_t tile_hint) {
+                 int64_t c_stride, int64_t tile_hint, int64_t pool_width, int pool_mode) {
+    // pool_width > 0: `out` is a float64 array of ceil(n / pool_width) bins per row; every tile is reduced on the
+    // device (mean or max over pool_width consecutive samples) and only the bins travel to the host
     gcwt_plan::HostStage& h = p->host;
     const auto t_begin = std::chrono::steady_clock::now();
     const int S = p->n_scales;
@@ -122,6 +126,16 @@ int host_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, i
         tile = std::min<int64_t>(n, (tile + 1023) / 1024 * 1024);
     }
     if (tile_hint > 0) tile = std::min<int64_t>(n, std::max<int64_t>(tile_hint, 1024));
+    const bool pooled = pool_width > 0;
+    if (pooled) {
+        if (p->out_kind == GCWT_OUT_COMPLEX) { set_error("execute_host: pooling needs amplitude or power output"); return GCWT_ERR_ARG; }
+        if (n_epochs != 1 || epochs[0] != 0 || epochs[1] != n) {
+            set_error("execute_host: pooling across epoch gaps is not supported (pool the full-rate result instead)");
+            return GCWT_ERR_UNSUPPORTED;
+        }
+        if (tile < n) tile = std::max<int64_t>(pool_width, tile / pool_width * pool_width);   // tiles end on bin boundaries
+    }
+    const int64_t bins_per_tile = pooled ? (tile + pool_width - 1) / pool_width : 0;
     const int64_t tile_alloc = (tile + 3) & ~int64_t(3);          // rows of a tile stay 16-byte aligned
     const size_t tile_bytes = (size_t)g * S * tile_alloc * out_el;
     int rc = grow_device(&h.d_in, &h.in_bytes, (size_t)g * n * in_el);
@@ -138,7 +152,17 @@ int host_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, i
         GCWT_CUDA_OK(cudaMalloc((void**)&h.d_means, sizeof(double) * g));
         h.means_cap = g;
     }
-    const bool direct = is_pinned(out);
+    if (pooled && h.pool_bytes < (size_t)g * S * bins_per_tile * sizeof(double)) {
+        const size_t need = (size_t)g * S * bins_per_tile * sizeof(double);
+        for (int b = 0; b < 2; ++b) {
+            if (h.d_pool[b]) { cudaFree(h.d_pool[b]); h.d_pool[b] = nullptr; }
+            if (h.h_pool[b]) { cudaFreeHost(h.h_pool[b]); h.h_pool[b] = nullptr; }
+            GCWT_CUDA_OK(cudaMalloc((void**)&h.d_pool[b], need));
+            GCWT_CUDA_OK(cudaMallocHost((void**)&h.h_pool[b], need));
+        }
+        h.pool_bytes = need;
+    }
+    const bool direct = pooled || is_pinned(out);
     if (!direct && h.ring_bytes < tile_bytes) {
         for (int b = 0; b < 2; ++b) {
             if (h.h_ring[b]) { cudaFreeHost(h.h_ring[b]); h.h_ring[b] = nullptr; }
@@ -154,7 +178,7 @@ int host_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, i
     const int n_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
 
     // zero rows outside the epochs (the reference starts from np.zeros, transforms.py:185)
-    {
+    if (!pooled) {
         int64_t pos = 0;
         for (int e = 0; e <= n_epochs; ++e) {
             const int64_t gap_end = e < n_epochs ? epochs[2 * e] : n;
@@ -167,11 +191,21 @@ int host_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, i
     }
 
     struct Pending { bool live = false; int64_t c0 = 0, gc = 0, a = 0, len = 0; };
+    auto drain_pool = [&](int b, const Pending& pd) {              // pooled tile: pinned staging -> the caller's float64 rows
+        const int64_t nb = (pd.len + pool_width - 1) / pool_width, b0 = pd.a / pool_width;
+        for (int64_t c = 0; c < pd.gc; ++c)
+            for (int s = 0; s < S; ++s)
+                memcpy((double*)out + (size_t)(pd.c0 + c) * c_stride + (size_t)s * s_stride + b0,
+                       h.h_pool[b] + ((size_t)c * S + s) * bins_per_tile, (size_t)nb * sizeof(double));
+    };
     Pending pend[2];
     std::thread copier[2];
     auto finish = [&](int b) -> int {                              // tile in slot b has reached the caller's array
         if (!pend[b].live) return GCWT_OK;
-        if (direct) {
+        if (pooled) {
+            GCWT_CUDA_OK(cudaEventSynchronize(h.ev_out[b]));
+            drain_pool(b, pend[b]);
+        } else if (direct) {
             GCWT_CUDA_OK(cudaEventSynchronize(h.ev_out[b]));
         } else if (copier[b].joinable()) {
             copier[b].join();
@@ -216,7 +250,14 @@ int host_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, i
                 GCWT_CUDA_OK(cudaEventRecord(h.ev_done[slot], h.st_compute));
                 GCWT_CUDA_OK(cudaStreamWaitEvent(h.st_copy, h.ev_done[slot], 0));
                 char* dst = (char*)out + ((size_t)c0 * c_stride + (size_t)a) * out_el;
-                if (direct) {
+                if (pooled) {
+                    rc = pool_rows_launch(h.d_out[slot], p->compute_type, gc * S, len, tile_alloc, pool_width, pool_mode, 0,
+                                          h.d_pool[slot], bins_per_tile, h.st_copy);
+                    if (rc) break;
+                    GCWT_CUDA_OK(cudaMemcpyAsync(h.h_pool[slot], h.d_pool[slot], (size_t)gc * S * bins_per_tile * sizeof(double),
+                                                 cudaMemcpyDeviceToHost, h.st_copy));
+                    GCWT_CUDA_OK(cudaEventRecord(h.ev_out[slot], h.st_copy));
+                } else if (direct) {
                     for (int64_t c = 0; c < gc; ++c)
                         GCWT_CUDA_OK(cudaMemcpy2DAsync(dst + (size_t)c * c_stride * out_el, (size_t)s_stride * out_el,
                                                        (const char*)h.d_out[slot] + (size_t)c * S * tile_alloc * out_el,
@@ -240,7 +281,7 @@ int host_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, i
                     });
                 }
                 pend[slot].live = true; pend[slot].c0 = c0; pend[slot].gc = gc; pend[slot].a = a; pend[slot].len = len;
-                bytes_out += (double)gc * S * len * out_el;
+                bytes_out += pooled ? (double)gc * S * ((len + pool_width - 1) / pool_width) * sizeof(double) : (double)gc * S * len * out_el;
                 ++n_tiles;
                 slot ^= 1;
             }

@@ -141,6 +141,7 @@ struct gcwt_plan {
         void* d_in = nullptr; size_t in_bytes = 0;           // the channel group's samples
         void* d_out[2] = {nullptr, nullptr}; size_t out_bytes = 0;   // double-buffered result tiles
         void* h_ring[2] = {nullptr, nullptr}; size_t ring_bytes = 0; // pinned bounce buffers (pageable destinations only)
+        double* d_pool[2] = {nullptr, nullptr}; double* h_pool[2] = {nullptr, nullptr}; size_t pool_bytes = 0;   // pooled tiles
         double* d_means = nullptr; int64_t means_cap = 0;
         cudaStream_t st_compute = nullptr, st_copy = nullptr;
         cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -177,6 +178,8 @@ int means_launch(const void* x, int in_type, int64_t n_channels, int64_t n_sampl
                  int64_t x_stride, double* d_means, double* partial, cudaStream_t st);
 int host_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, int64_t n_samples, int64_t x_stride,
                  const int64_t* epochs, int n_epochs, const double* means_host, void* out, int64_t s_stride,
-                 int64_t c_stride, int64_t tile_hint);
+                 int64_t c_stride, int64_t tile_hint, int64_t pool_width = 0, int pool_mode = 0);
+int pool_rows_launch(const void* x_dev, int type, int64_t n_rows, int64_t n_cols, int64_t row_stride, int64_t width,
+                     int mode, int square, double* out_dev, int64_t out_stride, cudaStream_t st);
 void host_stage_free(gcwt_plan* p);
 }  // namespace gcwt

@@ -239,4 +239,51 @@ int sig_moments(const void* x_dev, int type, int64_t n, int square, double* out_
     return GCWT_OK;
 }
 
+// ----------------------------------------------------------------------------- pooling for display
+// plot() draws contourf over the whole (scales, samples) array (ghost/wave/transforms.py:356-367,395-396);
+// a display has a few thousand columns.  One warp reduces one bin of `width` consecutive samples of one
+// row to its mean or maximum (of x, or of x^2 for power from amplitude), accumulating in fp64: the
+// consumer then pulls (rows x bins) values over PCIe instead of 4 bytes per coefficient.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_rows_kernel(const T* __restrict__ x, int64_t row_stride, int64_t n_cols, int64_t width, int mode, int square,
+                 double* __restrict__ out, int64_t out_stride, int64_t n_bins) {
+    const int64_t bin = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (bin >= n_bins) return;
+    const int64_t lo = bin * width, hi = min(n_cols, lo + width);
+    const T* row = x + (int64_t)blockIdx.y * row_stride;
+    double acc = mode == 1 ? -1.0e300 : 0.0;
+    for (int64_t i = lo + lane; i < hi; i += 32) {
+        double v = (double)row[i];
+        if (square) v *= v;
+        acc = mode == 1 ? fmax(acc, v) : acc + v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = mode == 1 ? fmax(acc, other) : acc + other;
+    }
+    if (lane == 0) out[(int64_t)blockIdx.y * out_stride + bin] = mode == 1 ? acc : acc / (double)(hi - lo);
+}
+
+int pool_rows_launch(const void* x_dev, int type, int64_t n_rows, int64_t n_cols, int64_t row_stride, int64_t width,
+                     int mode, int square, double* out_dev, int64_t out_stride, cudaStream_t st) {
+    if (n_rows <= 0 || n_cols <= 0 || width <= 0 || (mode != 0 && mode != 1)) { set_error("pool_rows: bad argument"); return GCWT_ERR_ARG; }
+    const int64_t n_bins = (n_cols + width - 1) / width;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += 65535) {                 // gridDim.y limit
+        const int64_t rows = std::min<int64_t>(65535, n_rows - r0);
+        dim3 grid((unsigned)((n_bins + 7) / 8), (unsigned)rows);
+        if (type == GCWT_F32)
+            pool_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)x_dev + r0 * row_stride, row_stride, n_cols, width, mode,
+                                                          square, out_dev + r0 * out_stride, out_stride, n_bins);
+        else
+            pool_rows_kernel<double><<<grid, 256, 0, st>>>((const double*)x_dev + r0 * row_stride, row_stride, n_cols, width,
+                                                           mode, square, out_dev + r0 * out_stride, out_stride, n_bins);
+        count_launch();
+    }
+    GCWT_CUDA_OK(cudaGetLastError());
+    return GCWT_OK;
+}
+
 }  // namespace gcwt

@@ -227,6 +227,59 @@ class CwtPlan:
                                               out.strides[0] // out.itemsize))
         return out
 
+    def execute_host_pooled(self, x, pool_width, pool="mean", means=None):
+        """As :meth:`execute_host` (one epoch, amplitude or power plans), but every tile is pooled on the
+        device: runs of ``pool_width`` consecutive samples are reduced to their mean (``pool='mean'``) or
+        maximum (``'max'``) and only those float64 bins cross the link.  Returns (channels, scales,
+        ceil(samples / pool_width)) float64 -- what a display of a few thousand columns needs
+        (reference plot: transforms.py:356-367,395-396)."""
+        if pool not in ("mean", "max"):
+            raise ValueError("pool must be 'mean' or 'max' but got {}".format(pool))
+        pool_width = int(pool_width)
+        if pool_width < 1:
+            raise ValueError("pool_width must be a positive integer")
+        x = np.asarray(x)
+        if x.ndim == 1:
+            x = x[None, :]
+        if x.dtype not in (np.float32, np.float64) or (self.dtype == np.float64 and x.dtype != np.float64):
+            x = x.astype(np.float64)
+        if x.strides[1] != x.itemsize:
+            x = np.ascontiguousarray(x)
+        n_ch, n = x.shape
+        n_bins = -(-n // pool_width)
+        out = np.empty((n_ch, self.n_scales, n_bins), dtype=np.float64)
+        mptr = None
+        if means is not None:
+            means = np.ascontiguousarray(means, dtype=np.float64)
+            mptr = means.ctypes.data
+        in_type = _lib.F32 if x.dtype == np.float32 else _lib.F64
+        _lib.check(self.lib.gcwt_execute_host_pooled(
+            self._h, x.ctypes.data, in_type, n_ch, n, x.strides[0] // x.itemsize, mptr, pool_width,
+            _lib.POOL_MEAN if pool == "mean" else _lib.POOL_MAX, out.ctypes.data, n_bins, n_bins * self.n_scales))
+        return out
+
+    def pool_rows(self, res, pool_width, pool="mean", square=False):
+        """Pool the last axis of a contiguous CUDA tensor (a device-resident result) in runs of ``pool_width``
+        samples: float64 CUDA tensor with ceil(n / pool_width) bins per row.  ``square`` pools the squares."""
+        torch = _torch()
+        if not res.is_cuda or res.is_complex() or res.dtype not in (torch.float32, torch.float64) or res.stride(-1) != 1:
+            raise ValueError("pool_rows needs a real float32 / float64 CUDA tensor with unit stride along the last axis")
+        if pool not in ("mean", "max"):
+            raise ValueError("pool must be 'mean' or 'max' but got {}".format(pool))
+        flat = res.reshape(-1, res.shape[-1]) if res.is_contiguous() else None
+        if flat is None:
+            if res.dim() != 2:
+                raise ValueError("pool_rows needs a contiguous tensor (or a 2-D one with a row stride)")
+            flat = res
+        n_rows, n = flat.shape
+        n_bins = -(-n // int(pool_width))
+        out = torch.empty((n_rows, n_bins), dtype=torch.float64, device=res.device)
+        st = torch.cuda.current_stream(res.device).cuda_stream
+        _lib.check(self.lib.gcwt_pool_rows(flat.data_ptr(), _lib.F32 if res.dtype == torch.float32 else _lib.F64, n_rows, n,
+                                           flat.stride(0), int(pool_width), _lib.POOL_MEAN if pool == "mean" else _lib.POOL_MAX,
+                                           1 if square else 0, out.data_ptr(), n_bins, self.device, st))
+        return out.reshape(tuple(res.shape[:-1]) + (n_bins,))
+
     def host_stats(self):
         """{wall_ms, pinned_destination, tiles, bytes_out} of the last execute_host."""
         v = (C.c_double * 4)()

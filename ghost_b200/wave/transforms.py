@@ -139,7 +139,7 @@ class ContinuousWaveletTransform(WaveletTransform):
     # ------------------------------------------------------------------ transform
     def transform(self, data, *, timestamps=None, fs=None, freq_limits=None, freqs=None,
                   voices_per_octave=None, parallel=None, verbose=None, multichannel=None,
-                  keep_on_device=None, out=None, **kwargs):
+                  keep_on_device=None, out=None, pool_width=None, pool=None, **kwargs):
         """Continuous wavelet transform of one recording.
 
         Parameters as the reference (transforms.py:59-106): ``data`` is an ndarray with
@@ -155,7 +155,10 @@ class ContinuousWaveletTransform(WaveletTransform):
         shape (channels, scales, samples).  ``out`` is an optional preallocated result array
         ((scales, samples), or (channels, scales, samples) with ``multichannel``) of the output dtype;
         a pinned one is written by DMA.  ``keep_on_device=True`` leaves the result on the GPU instead
-        (``device_result``; it must then fit in device memory).
+        (``device_result``; it must then fit in device memory).  ``pool_width=w`` (with ``pool='mean'`` or
+        ``'max'``) is for displays: the result is reduced on the device over runs of ``w`` samples, the
+        arrays read back have ceil(samples / w) columns (float64) and ``time`` holds the bin centres --
+        the link then carries kilobytes instead of every coefficient.
 
         Returns None; results are read from the properties.
         """
@@ -229,7 +232,23 @@ class ContinuousWaveletTransform(WaveletTransform):
         self._host = None
         self._result = None
         start_time = _time.time()
-        if not keep_on_device:
+        if pool_width is not None:
+            if keep_on_device or out is not None:
+                raise ValueError("'pool_width' cannot be combined with 'keep_on_device' or 'out'")
+            if self._output == "complex":
+                raise ValueError("'pool_width' needs output='amplitude' or 'power'")
+            if len(epoch_bounds) != 1:
+                raise ValueError("'pool_width' needs gap-free timestamps (one epoch)")
+            x_in = x_host if x_host.dtype == in_dtype else x_host.astype(in_dtype)
+            res = plan.execute_host_pooled(x_in, pool_width, "mean" if pool is None else pool)
+            self._host = res if multichannel else res[0]
+            w = int(pool_width)
+            n_all = x_host.shape[1]
+            edges = np.minimum(np.arange(0, n_all + w, w), n_all)
+            ts = np.asarray(self._time, dtype=np.float64)
+            self._time = np.array([ts[a:b].mean() for a, b in zip(edges[:-1], edges[1:]) if b > a])
+            self._time_auto = None
+        elif not keep_on_device:
             # host arrays in, host arrays out (what the reference returns, transforms.py:185,231): one
             # streamed call into the library -- tiles of the result travel to the host while the next is
             # computed, so results larger than device memory work
@@ -392,9 +411,21 @@ class ContinuousWaveletTransform(WaveletTransform):
         return slice(n - f1, n - f0)
 
     # ------------------------------------------------------------------ plot
-    def spectrogram_data(self, *, kind=None, standardize=None, time_limits=None, freq_limits=None):
+    def spectrogram_data(self, *, kind=None, standardize=None, time_limits=None, freq_limits=None, max_points=None,
+                         pool=None):
         """The arrays ``plot`` draws: (time, frequencies, data) after the same selection and
-        optional global standardisation as the reference (transforms.py:356-367)."""
+        optional global standardisation as the reference (transforms.py:356-367).
+
+        ``max_points``: at most that many columns -- the selected window is pooled over runs of
+        ceil(columns / max_points) samples (``pool='mean'`` or ``'max'``; on the device when the result is
+        still there, so that only the pooled window is copied to the host) and the time axis holds the
+        bin centres.  Standardisation uses the statistics of the full-rate array, as the reference does."""
+        if pool is None:
+            pool = "mean"
+        if pool not in ("mean", "max"):
+            raise ValueError("'pool' must be 'mean' or 'max' but got {}".format(pool))
+        if max_points is not None and int(max_points) < 1:
+            raise ValueError("'max_points' must be a positive integer")
         if kind is None:
             kind = "amplitude"
         if kind not in ("amplitude", "power"):
@@ -407,21 +438,43 @@ class ContinuousWaveletTransform(WaveletTransform):
             raise ValueError("plotting needs a single-channel transform")
         time_slice = slice(None) if time_limits is None else self._restrict_plot_time(np.array(time_limits))
         freq_slice = slice(None) if freq_limits is None else self._restrict_plot_freq(freq_limits)
+        tvec = np.asarray(self._time)[time_slice]
+        width = 1 if max_points is None else max(1, -(-len(tvec) // int(max_points)))
+
+        def pooled_time():
+            edges = np.minimum(np.arange(0, len(tvec) + width, width), len(tvec))
+            return np.array([tvec[a:b].mean() for a, b in zip(edges[:-1], edges[1:]) if b > a])
+
         if self._result is not None and self._host is None and self._output in ("amplitude", "power") \
                 and (self._output == kind or (self._output == "amplitude" and kind == "power")):
             # result still on the device (keep_on_device=True): global moments there, and only the
-            # requested window is copied to the host
-            win = self._result[0][freq_slice, time_slice].cpu().numpy()
-            if kind == "power" and self._output == "amplitude":
-                win = np.square(win)
+            # requested (pooled) window is copied to the host
+            sq = kind == "power" and self._output == "amplitude"
+            if width > 1:
+                dev_win = self._result[0][freq_slice, time_slice]
+                win = self.last_plan.pool_rows(dev_win, width, pool, square=sq).cpu().numpy()
+                tvec = pooled_time()
+            else:
+                win = self._result[0][freq_slice, time_slice].cpu().numpy()
+                if sq:
+                    win = np.square(win)
             if standardize:
-                mean, std = self.device_moments(square=(kind == "power" and self._output == "amplitude"))
+                mean, std = self.device_moments(square=sq)
                 win = (win - mean) / std
-            return self._time[time_slice], self._frequencies[freq_slice], win
+            return tvec, self._frequencies[freq_slice], win
         data = self.amplitude if kind == "amplitude" else self.power
+        mean, std = (data.mean(), data.std()) if standardize else (0.0, 1.0)
+        win = data[freq_slice, time_slice]
+        if width > 1:
+            nb = -(-win.shape[1] // width)
+            pad = nb * width - win.shape[1]
+            fill = np.nan if pool == "mean" else -np.inf
+            wp = np.concatenate([win.astype(np.float64), np.full((win.shape[0], pad), fill)], axis=1).reshape(win.shape[0], nb, width)
+            win = np.nanmean(wp, axis=2) if pool == "mean" else wp.max(axis=2)
+            tvec = pooled_time()
         if standardize:
-            data = (data - data.mean()) / data.std()
-        return self._time[time_slice], self._frequencies[freq_slice], data[freq_slice, time_slice]
+            win = (win - mean) / std
+        return tvec, self._frequencies[freq_slice], win
 
     def device_moments(self, square=False):
         """(mean, std) in float64 over the whole device-resident result (of its square when
@@ -442,8 +495,9 @@ class ContinuousWaveletTransform(WaveletTransform):
         return float(out[0]), float(out[1])
 
     def plot(self, *, kind=None, timescale=None, logscale=None, standardize=None, relative_time=None,
-             center_time=None, time_limits=None, freq_limits=None, ax=None, **kwargs):
-        """Filled-contour spectrogram (transforms.py:233-402).  Needs matplotlib."""
+             center_time=None, time_limits=None, freq_limits=None, ax=None, max_points=None, pool=None, **kwargs):
+        """Filled-contour spectrogram (transforms.py:233-402).  Needs matplotlib.  ``max_points`` / ``pool``:
+        see :meth:`spectrogram_data` (pooling to the display's resolution, on the device when possible)."""
         if timescale is None:
             timescale = "seconds"
         if timescale not in ("milliseconds", "seconds", "minutes", "hours"):
@@ -474,8 +528,8 @@ class ContinuousWaveletTransform(WaveletTransform):
             else:
                 raise TypeError("'time_limits' must be of type nelpy.EpochArray or np.ndarray but got"
                                 " {}".format(type(time_limits)))
-        timevec, freqvec, data = self.spectrogram_data(kind=kind, standardize=standardize,
-                                                       time_limits=time_limits, freq_limits=freq_limits)
+        timevec, freqvec, data = self.spectrogram_data(kind=kind, standardize=standardize, time_limits=time_limits,
+                                                       freq_limits=freq_limits, max_points=max_points, pool=pool)
         kind = "amplitude" if kind is None else kind
         title = "Wavelet Amplitude Spectrogram" if kind == "amplitude" else "Wavelet Power Spectrogram"
         scale, xlabel = {"milliseconds": (1000.0, "Time (msec)"), "seconds": (1.0, "Time (sec)"),

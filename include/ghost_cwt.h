@@ -132,6 +132,26 @@ int gcwt_execute_host(gcwt_plan *plan, const void *x, int32_t in_type,
                       const double *means_host,
                       void *out, int64_t out_scale_stride, int64_t out_channel_stride);
 
+/* Pooling for display.  plot() draws the whole (scales, samples) array (ghost/wave/transforms.py:356-367,
+ * 395-396) although a display has a few thousand columns: these reduce every run of pool_width consecutive
+ * samples of a row to its mean (GCWT_POOL_MEAN) or maximum (GCWT_POOL_MAX), in fp64, on the device.
+ *
+ * gcwt_pool_rows: device array of n_rows rows (row_stride elements apart) of n_cols samples ->
+ *   out_dev[row * out_stride + bin], ceil(n_cols / pool_width) float64 bins per row; square != 0 pools x^2
+ *   (power from an amplitude array).
+ * gcwt_execute_host_pooled: gcwt_execute_host (one epoch, amplitude or power plans) whose tiles are pooled
+ *   on the device, so that only ceil(n_samples / pool_width) float64 bins per (channel, scale) cross the
+ *   link instead of every coefficient: out[c * out_channel_stride + s * out_scale_stride + bin]. */
+#define GCWT_POOL_MEAN 0
+#define GCWT_POOL_MAX  1
+int gcwt_pool_rows(const void *x_dev, int32_t type, int64_t n_rows, int64_t n_cols, int64_t row_stride,
+                   int64_t pool_width, int32_t pool_mode, int32_t square, double *out_dev, int64_t out_stride,
+                   int32_t device, void *stream);
+int gcwt_execute_host_pooled(gcwt_plan *plan, const void *x, int32_t in_type,
+                             int64_t n_channels, int64_t n_samples, int64_t x_stride,
+                             const double *means_host, int64_t pool_width, int32_t pool_mode,
+                             double *out, int64_t out_scale_stride, int64_t out_channel_stride);
+
 /* Diagnostics of the last gcwt_execute_host: out4 = {wall ms, 1 if `out` was pinned (direct DMA) else 0,
  * tiles, bytes copied to the host}. */
 int gcwt_host_stats(const gcwt_plan *plan, double *out4);
