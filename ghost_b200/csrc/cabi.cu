@@ -79,6 +79,13 @@ int sig_fastconv_host(const double* sig_host, int sig_complex, int64_t n, const 
 
 int sig_moments(const void* x_dev, int type, int64_t n, int square, double* out_host, cudaStream_t st);
 
+// Every entry point selects the plan's device; the caller's current device is restored on return.
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static int check_exec_args(const gcwt_plan* plan, const void* x, int in_type, int64_t n_channels,
                            int64_t n_samples, int64_t x_stride, const void* out) {
     if (!plan) { set_error("plan is NULL"); return GCWT_ERR_ARG; }
@@ -121,7 +128,7 @@ int gcwt_plan_create(gcwt_plan** out, const gcwt_plan_desc* d) {
         return GCWT_ERR_CUDA;
     }
     if (d->device < 0 || d->device >= ndev) { set_error("plan_create: bad device ordinal"); return GCWT_ERR_ARG; }
-    GCWT_CUDA_OK(cudaSetDevice(d->device));
+    DeviceScope dev_scope(d->device);
 
     gcwt_plan* p = new (std::nothrow) gcwt_plan();
     if (!p) { set_error("out of host memory"); return GCWT_ERR_NOMEM; }
@@ -174,7 +181,7 @@ int gcwt_plan_create(gcwt_plan** out, const gcwt_plan_desc* d) {
 
 int gcwt_plan_destroy(gcwt_plan* p) {
     if (!p) return GCWT_OK;
-    cudaSetDevice(p->device);
+    DeviceScope dev_scope(p->device);
     prof_collect(p);
     host_stage_free(p);
     fast_plan_free(p);
@@ -204,7 +211,7 @@ int gcwt_profile_enable(gcwt_plan* p, int32_t on) {
 
 int gcwt_profile_read(gcwt_plan* p, double* ms_out, int64_t* launches_out, int32_t reset) {
     if (!p || !ms_out || !launches_out) { set_error("profile_read: NULL argument"); return GCWT_ERR_ARG; }
-    cudaSetDevice(p->device);
+    DeviceScope dev_scope(p->device);
     prof_collect(p);
     if (getenv("GCWT_CLASS_TIMES")) {                  // developer aid: per-class milliseconds since the last reset
         for (int t = 0; t < 64; ++t)
@@ -242,7 +249,7 @@ int gcwt_channel_means(const void* x, int32_t in_type, int64_t n_channels, int64
                        int64_t x_stride, double* means_dev, int32_t device, void* stream) {
     if (!x || !means_dev) { set_error("channel_means: NULL argument"); return GCWT_ERR_ARG; }
     if (in_type != GCWT_F32 && in_type != GCWT_F64) { set_error("channel_means: bad in_type"); return GCWT_ERR_ARG; }
-    GCWT_CUDA_OK(cudaSetDevice(device));
+    DeviceScope dev_scope(device);
     // stand-alone call: scratch is allocated and freed here (synchronous; not on the transform path)
     double* partial = nullptr;
     GCWT_CUDA_OK(cudaMalloc((void**)&partial, sizeof(double) * means_blocks(n_samples) * n_channels));
@@ -258,7 +265,11 @@ int gcwt_execute(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_channel
     int rc = check_exec_args(p, x, in_type, n_channels, n_samples, x_stride, out);
     if (rc) return rc;
     if (halo_left < 0 || halo_right < 0) { set_error("execute: negative halo"); return GCWT_ERR_ARG; }
-    GCWT_CUDA_OK(cudaSetDevice(p->device));
+    if (n_channels > 1 && x_stride < n_samples + halo_left + halo_right) {
+        set_error("execute: x_stride smaller than n_samples plus the halos (channels would overlap)"); return GCWT_ERR_ARG;
+    }
+    if (out_scale_stride < n_samples) { set_error("execute: out_scale_stride smaller than n_samples"); return GCWT_ERR_ARG; }
+    DeviceScope dev_scope(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const double* d_means = means;
     if (!d_means) {
@@ -311,7 +322,7 @@ int gcwt_execute_host(gcwt_plan* p, const void* x, int32_t in_type, int64_t n_ch
     int rc = check_exec_args(p, x, in_type, n_channels, n_samples, x_stride, out);
     if (rc) return rc;
     if (out_scale_stride < n_samples) { set_error("execute_host: out_scale_stride smaller than n_samples"); return GCWT_ERR_ARG; }
-    GCWT_CUDA_OK(cudaSetDevice(p->device));
+    DeviceScope dev_scope(p->device);
     int64_t tile_hint = 0;
     if (const char* e = getenv("GCWT_HOST_TILE")) tile_hint = atoll(e);       // developer aid: force the time tile
     return host_execute(p, x, in_type, n_channels, n_samples, x_stride, epoch_bounds, n_epochs, means_host, out,
@@ -325,7 +336,7 @@ int gcwt_execute_host_pooled(gcwt_plan* p, const void* x, int32_t in_type, int64
     if (rc) return rc;
     if (pool_width < 1 || (pool_mode != GCWT_POOL_MEAN && pool_mode != GCWT_POOL_MAX)) { set_error("execute_host_pooled: bad pool_width / pool_mode"); return GCWT_ERR_ARG; }
     if (out_scale_stride < (n_samples + pool_width - 1) / pool_width) { set_error("execute_host_pooled: out_scale_stride smaller than the bin count"); return GCWT_ERR_ARG; }
-    GCWT_CUDA_OK(cudaSetDevice(p->device));
+    DeviceScope dev_scope(p->device);
     int64_t tile_hint = 0;
     if (const char* e = getenv("GCWT_HOST_TILE")) tile_hint = atoll(e);
     return host_execute(p, x, in_type, n_channels, n_samples, x_stride, nullptr, 0, means_host, out, out_scale_stride,
@@ -335,7 +346,7 @@ int gcwt_execute_host_pooled(gcwt_plan* p, const void* x, int32_t in_type, int64
 int gcwt_pool_rows(const void* x_dev, int32_t type, int64_t n_rows, int64_t n_cols, int64_t row_stride, int64_t pool_width,
                    int32_t pool_mode, int32_t square, double* out_dev, int64_t out_stride, int32_t device, void* stream) {
     if (!x_dev || !out_dev || (type != GCWT_F32 && type != GCWT_F64)) { set_error("pool_rows: bad argument"); return GCWT_ERR_ARG; }
-    GCWT_CUDA_OK(cudaSetDevice(device));
+    DeviceScope dev_scope(device);
     return pool_rows_launch(x_dev, type, n_rows, n_cols, row_stride, pool_width, pool_mode, square, out_dev, out_stride,
                             (cudaStream_t)stream);
 }
@@ -356,7 +367,7 @@ int gcwt_filter_response(int64_t length, int32_t k_first, int32_t n_terms, const
     if (!terms || !out_host || length < 1 || n_terms < 1 || n_fft < length || n_bins < 1 || first_bin < 0) {
         set_error("filter_response: bad argument"); return GCWT_ERR_ARG;
     }
-    GCWT_CUDA_OK(cudaSetDevice(device));
+    DeviceScope dev_scope(device);
     return filter_response_device(length, k_first, n_terms, terms, n_fft, first_bin, n_bins, out_host);
 }
 
@@ -365,33 +376,33 @@ int gcwt_morse_kernel(int64_t length, int32_t k_first, int32_t n_terms, const do
     if (!terms || !out_host || length < 1 || n_terms < 1 || k_first < 0) {
         set_error("morse_kernel: bad argument"); return GCWT_ERR_ARG;
     }
-    GCWT_CUDA_OK(cudaSetDevice(device));
+    DeviceScope dev_scope(device);
     return morse_kernel_device(length, k_first, n_terms, terms, out_host);
 }
 
 int gcwt_fastconv(const double* signal, int32_t signal_is_complex, int64_t n, const double* kernel,
                   int32_t kernel_is_complex, int64_t m, double* out_full, int32_t device) {
     if (!signal || !kernel || !out_full || n < 1 || m < 1) { set_error("fastconv: bad argument"); return GCWT_ERR_ARG; }
-    GCWT_CUDA_OK(cudaSetDevice(device));
+    DeviceScope dev_scope(device);
     return sig_fastconv_host(signal, signal_is_complex, n, kernel, kernel_is_complex, m, out_full);
 }
 
 int gcwt_dft(const double* x_complex, int64_t n, int32_t sign, double* out_complex, int32_t device) {
     if (!x_complex || !out_complex || n < 1 || (sign != 1 && sign != -1)) { set_error("dft: bad argument"); return GCWT_ERR_ARG; }
-    GCWT_CUDA_OK(cudaSetDevice(device));
+    DeviceScope dev_scope(device);
     return sig_dft_host(x_complex, n, sign, out_complex);
 }
 
 int gcwt_moments(const void* x_dev, int32_t type, int64_t n, int32_t square, double* out_host, int32_t device,
                  void* stream) {
     if (!x_dev || !out_host || n < 1 || (type != GCWT_F32 && type != GCWT_F64)) { set_error("moments: bad argument"); return GCWT_ERR_ARG; }
-    GCWT_CUDA_OK(cudaSetDevice(device));
+    DeviceScope dev_scope(device);
     return sig_moments(x_dev, type, n, square, out_host, (cudaStream_t)stream);
 }
 
 int gcwt_analytic_signal(const double* x, int64_t n, double* out_complex, int32_t device) {
     if (!x || !out_complex || n < 1) { set_error("analytic_signal: bad argument"); return GCWT_ERR_ARG; }
-    GCWT_CUDA_OK(cudaSetDevice(device));
+    DeviceScope dev_scope(device);
     return sig_analytic_host(x, n, out_complex);
 }
 

@@ -20,6 +20,21 @@ void set_error(const std::string& msg);     // defined in cabi.cu (thread-local)
         }                                                                         \
     } while (0)
 
+// scratch device memory of the stand-alone helpers: freed on every return path
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); set_error("device allocation of scratch memory failed"); return GCWT_ERR_NOMEM; }
+        return GCWT_OK;
+    }
+    double2* c() { return (double2*)p; }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
 // ---------------------------------------------------------------- complex
 template <typename T> struct cplx_of;
 template <> struct cplx_of<float>  { typedef float2  type; };

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "multiplier.cuh"
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -479,7 +480,10 @@ int fast_plan_build(gcwt_plan* p) {
         const std::vector<int>& ids = kv.second;
         const int cap = level >= 0 ? kMaxClassScales : kMaxFullScales;
         for (size_t i0 = 0; i0 < ids.size(); i0 += cap) {
-            FastClass fc;
+            // the class enters the plan's list before its device tables are allocated, so that an error
+            // return below leaves them to fast_plan_free
+            p->classes.emplace_back();
+            FastClass& fc = p->classes.back();
             fc.level = level;
             fc.nc_full = level >= 0 ? ((int64_t)kChunkDec << level) : kFullN;
             fc.scale_ids.assign(ids.begin() + i0, ids.begin() + std::min(ids.size(), i0 + cap));
@@ -570,7 +574,6 @@ int fast_plan_build(gcwt_plan* p) {
             }
             GCWT_CUDA_OK(cudaMalloc((void**)&fc.d_scale_ids, sizeof(int32_t) * ns));
             GCWT_CUDA_OK(cudaMemcpy(fc.d_scale_ids, fc.scale_ids.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice));
-            p->classes.push_back(fc);
         }
     }
     if (p->guard && !p->classes.empty()) {
@@ -1616,7 +1619,7 @@ fused_full_kernel(const FusedParams prm) {
 // ============================================================================ driver
 template <int KIND, int LP, bool GUARD>
 static void launch_banded_g(unsigned nblk, cudaStream_t st, const FusedParams& prm) {
-    static bool attr_set[64] = {false};
+    static std::atomic<bool> attr_set[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
@@ -1647,7 +1650,7 @@ static void launch_banded(int kind, int lp, unsigned nblk, cudaStream_t st, cons
 
 template <typename TIn, int KIND, bool GUARD>
 static void launch_full_g(unsigned nblk, cudaStream_t st, const FusedParams& prm) {
-    static bool attr_set[64] = {false};
+    static std::atomic<bool> attr_set[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
@@ -1999,7 +2002,7 @@ int guard_resolve(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, 
     return GCWT_OK;
 }
 
-static bool g_attr_done[64] = {false};
+static std::atomic<bool> g_attr_done[64];
 
 template <typename TIn>
 static int set_smem_attrs() {

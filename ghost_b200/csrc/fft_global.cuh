@@ -26,7 +26,8 @@ __global__ void stockham_pass_kernel(const typename cplx_of<T>::type* __restrict
 #pragma unroll
         for (int r = 1; r < R; ++r) {
             const int e = (int)(((int64_t)r * k) % span);
-            C w = expipi((T)(SIGN * 2) * (T)e / (T)span);
+            // the ratio is formed in fp64: e and span are not exact in fp32 once n exceeds 2^24
+            C w = expipi((T)((double)(SIGN * 2) * (double)e / (double)span));
             v[r] = cmul(v[r], w);
         }
     }

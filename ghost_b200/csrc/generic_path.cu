@@ -403,18 +403,15 @@ __global__ void filter_response_kernel(int64_t L, int k_first, int n_terms, cons
 
 int filter_response_device(int64_t L, int k_first, int n_terms, const double* terms_host, int64_t nfft,
                            int64_t first_bin, int64_t n_bins, double* out_host) {
-    double* d_terms = nullptr;
-    double2* d_out = nullptr;
-    GCWT_CUDA_OK(cudaMalloc((void**)&d_terms, sizeof(double) * n_terms));
-    GCWT_CUDA_OK(cudaMalloc((void**)&d_out, sizeof(double2) * n_bins));
-    GCWT_CUDA_OK(cudaMemcpy(d_terms, terms_host, sizeof(double) * n_terms, cudaMemcpyHostToDevice));
-    filter_response_kernel<<<(unsigned)((n_bins + 255) / 256), 256>>>(L, k_first, n_terms, d_terms, nfft,
-                                                                       first_bin, n_bins, d_out);
+    DevBuf terms, out;
+    { int rc = terms.alloc(sizeof(double) * n_terms); if (rc) return rc; }
+    { int rc = out.alloc(sizeof(double2) * n_bins); if (rc) return rc; }
+    GCWT_CUDA_OK(cudaMemcpy(terms.p, terms_host, sizeof(double) * n_terms, cudaMemcpyHostToDevice));
+    filter_response_kernel<<<(unsigned)((n_bins + 255) / 256), 256>>>(L, k_first, n_terms, terms.as<double>(), nfft,
+                                                                       first_bin, n_bins, out.as<double2>());
     count_launch();
     GCWT_CUDA_OK(cudaGetLastError());
-    GCWT_CUDA_OK(cudaMemcpy(out_host, d_out, sizeof(double2) * n_bins, cudaMemcpyDeviceToHost));
-    cudaFree(d_terms);
-    cudaFree(d_out);
+    GCWT_CUDA_OK(cudaMemcpy(out_host, out.p, sizeof(double2) * n_bins, cudaMemcpyDeviceToHost));
     return GCWT_OK;
 }
 
@@ -437,17 +434,14 @@ __global__ void morse_kernel_kernel(int64_t L, int k_first, int n_terms, const d
 }
 
 int morse_kernel_device(int64_t L, int k_first, int n_terms, const double* terms_host, double* out_host) {
-    double* d_terms = nullptr;
-    double2* d_out = nullptr;
-    GCWT_CUDA_OK(cudaMalloc((void**)&d_terms, sizeof(double) * n_terms));
-    GCWT_CUDA_OK(cudaMalloc((void**)&d_out, sizeof(double2) * L));
-    GCWT_CUDA_OK(cudaMemcpy(d_terms, terms_host, sizeof(double) * n_terms, cudaMemcpyHostToDevice));
-    morse_kernel_kernel<<<(unsigned)((L + 255) / 256), 256>>>(L, k_first, n_terms, d_terms, d_out);
+    DevBuf terms, out;
+    { int rc = terms.alloc(sizeof(double) * n_terms); if (rc) return rc; }
+    { int rc = out.alloc(sizeof(double2) * L); if (rc) return rc; }
+    GCWT_CUDA_OK(cudaMemcpy(terms.p, terms_host, sizeof(double) * n_terms, cudaMemcpyHostToDevice));
+    morse_kernel_kernel<<<(unsigned)((L + 255) / 256), 256>>>(L, k_first, n_terms, terms.as<double>(), out.as<double2>());
     count_launch();
     GCWT_CUDA_OK(cudaGetLastError());
-    GCWT_CUDA_OK(cudaMemcpy(out_host, d_out, sizeof(double2) * L, cudaMemcpyDeviceToHost));
-    cudaFree(d_terms);
-    cudaFree(d_out);
+    GCWT_CUDA_OK(cudaMemcpy(out_host, out.p, sizeof(double2) * L, cudaMemcpyDeviceToHost));
     return GCWT_OK;
 }
 

@@ -82,16 +82,6 @@ __global__ void st_hilbert_weights(C* __restrict__ X, int64_t n) {
 
 static inline unsigned nblk(int64_t m) { return (unsigned)((m + 255) / 256); }
 
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) {
-        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); set_error("sigtools: device allocation failed"); return GCWT_ERR_NOMEM; }
-        return GCWT_OK;
-    }
-    C* c() { return (C*)p; }
-};
-
 // Power-of-two FFT of `m` points: result pointer returned in `res` (one of a / b).
 template <int SIGN>
 static void fft_pow2(C* a, C* b, int64_t m, C*& res) {
@@ -219,8 +209,9 @@ __global__ void moments_kernel(const T* __restrict__ x, int64_t n, int square, d
 }
 
 int sig_moments(const void* x_dev, int type, int64_t n, int square, double* out_host, cudaStream_t st) {
-    double* d = nullptr;
-    GCWT_CUDA_OK(cudaMalloc((void**)&d, 2 * sizeof(double)));
+    DevBuf buf;
+    { int rc = buf.alloc(2 * sizeof(double)); if (rc) return rc; }
+    double* d = buf.as<double>();
     GCWT_CUDA_OK(cudaMemsetAsync(d, 0, 2 * sizeof(double), st));
     const unsigned blocks = (unsigned)std::min<int64_t>(148 * 8, (n + 255) / 256);
     if (type == GCWT_F32) moments_kernel<float><<<blocks, 256, 0, st>>>((const float*)x_dev, n, square, d);
@@ -230,7 +221,6 @@ int sig_moments(const void* x_dev, int type, int64_t n, int square, double* out_
     double h[2];
     GCWT_CUDA_OK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st));
     GCWT_CUDA_OK(cudaStreamSynchronize(st));
-    cudaFree(d);
     const double mean = h[0] / (double)n;
     double var = h[1] / (double)n - mean * mean;
     if (var < 0.0) var = 0.0;

@@ -17,6 +17,11 @@
  * passed in through gcwt_plan_desc together with the non-zero samples X[k] of each
  * scale's L-point Morse spectrum (morseutils.py:129-133,178).
  *
+ * Threading: a plan owns its workspace, per-call accumulators, side streams and staging buffers, so it
+ * serves ONE gcwt_execute / gcwt_execute_host at a time (calls on one plan from several threads or
+ * streams must be serialised by the caller; different plans are independent).  Every entry point
+ * selects the plan's device and restores the caller's current device before returning.
+ *
  * All functions return 0 on success or a negative GCWT_ERR_* code; the message for the
  * last failure on the calling thread is available from gcwt_last_error().  There is no
  * CPU fallback: every entry point that computes needs a CUDA device.

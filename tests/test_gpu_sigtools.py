@@ -87,3 +87,24 @@ def test_argument_errors():
         sigtools.fastconv(np.zeros(3), np.zeros(5), mode="valid")
     with pytest.raises(ValueError):
         sigtools.chirpz_dft(np.zeros((3, 3)))
+
+
+def test_fastconv_freq_keeps_the_reference_wraparound():
+    """the reference multiplies every block's spectrum by kernel_fd as it is
+    (ghost/sigtools/convolution.py:263-273), i.e. convolves circularly with the WHOLE inverse DFT of
+    kernel_fd; taps beyond kernel_len therefore wrap around.  Same here (numpy restatement of that loop)."""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(5000)
+    taps = rng.standard_normal(700) * np.hanning(700)              # 700 real taps, but the caller claims 400
+    nfd, m = 1500, 400
+    Y = np.fft.fft(taps, nfd)
+    res = np.zeros(len(x) + m - 1, dtype=complex)
+    chunk = min(nfd - m + 1, len(x))
+    for start in range(0, len(x), chunk):
+        length = min(chunk, len(x) - start)
+        conv = np.fft.ifft(np.fft.fft(x[start:start + length], n=nfd) * Y)[:length + m - 1]
+        res[start:start + len(conv)] += conv
+    for mode, sl in (("full", slice(None)), ("same", slice((m - 1) // 2, (m - 1) // 2 + len(x)))):
+        got = sigtools.fastconv_freq_fftw(x, Y, m, mode=mode, n_threads=4)
+        assert np.allclose(got, res[sl], rtol=1e-10, atol=1e-10)
+    assert not np.allclose(res[(m - 1) // 2:(m - 1) // 2 + len(x)], np.convolve(x, taps[:m])[(m - 1) // 2:(m - 1) // 2 + len(x)])
