@@ -764,6 +764,11 @@ template <> struct out_elem<GCWT_OUT_COMPLEX> { typedef float2 type; };
 // Epilogue (kernel (3)): complex, |W| or |W|^2 of 16 register-resident outputs that lie
 // `stride` elements apart; bit k of `mask` says whether output k is owned by this chunk.
 __device__ __forceinline__ void st_pred(float* p, float v, unsigned on) {
+#ifdef GCWT_EXP_CSSTORE
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.f32 [%0], %1;\n\t}"
+                 :: "l"(p), "f"(v), "r"(on) : "memory");
+    return;
+#endif
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}"
                  :: "l"(p), "f"(v), "r"(on) : "memory");
 }
@@ -1518,12 +1523,18 @@ __device__ __forceinline__ void full_scale_loop(const FusedParams& prm, const fl
         // the issue slots, not by this latency -- staging the rows ahead of time changed nothing
         // measurable, neither with cp.async (a second LSU operation per entry) nor with a TMA bulk
         // copy + mbarrier one scale ahead (8.89 vs 8.92 ms on config 2)
+#ifdef GCWT_EXP_TABLE0
+        const float2* tab = prm.table + tid;                         // what-if: every scale reads the same (L1-hot) row
+#else
         const float2* tab = prm.table + (int64_t)s * kFullN + tid;
+#endif
         if (nmu == 2) full_prepass<2>(Yf, tab, A, tw4k);
         else if (nmu == 4) full_prepass<4>(Yf, tab, A, tw4k);
         else if (nmu == 8) full_prepass<8>(Yf, tab, A, tw4k);
         else full_prepass<16>(Yf, tab, A, tw4k);
+#ifndef GCWT_EXP_NOBAR
         __syncthreads();
+#endif
         if (MEASURE && s > 0 && tid == 0) {                          // every add for scale s - 1 came before this barrier
             atomicAdd(prm.pow + (blockIdx.x / prm.n_chunks) * prm.pow_stride + s_ids[s - 1], s_pow[(s - 1) & 1] * prm.pow_weight);
             s_pow[(s - 1) & 1] = 0.f;
@@ -1536,12 +1547,38 @@ __device__ __forceinline__ void full_scale_loop(const FusedParams& prm, const fl
         e[0] = a[0];
 #pragma unroll
         for (int k = 1; k < 16; ++k) e[k * 16] = cmul(a[k], tw[k]);
+#ifndef GCWT_EXP_NOBAR
         __syncthreads();
+#endif
         const float2* e2 = ex + g * 16 + r;
 #pragma unroll
         for (int k = 0; k < 16; ++k) a[k] = e2[k * 256];
+#ifndef GCWT_EXP_NOPASS2
         dft16<+1>(a);
+#endif
+#ifdef GCWT_EXP_NOSTORE
+        store_column<KIND>(out_c + (int64_t)s_ids[s] * prm.s_stride + rel, 256, mask & 1u, a);
+#elif defined(GCWT_EXP_HALFSTORE)
+        store_column<KIND>(out_c + (int64_t)s_ids[s] * prm.s_stride + rel, 256, mask & 0x5555u, a);     // what-if: 8 of the 16 stores
+#elif defined(GCWT_EXP_B16STORE)
+        {   // what-if: 16 stores of 2 bytes each (same requests, half the sectors)
+            unsigned short* o16 = (unsigned short*)(out_c + (int64_t)s_ids[s] * prm.s_stride) + rel;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (mask & (1u << k)) o16[k * 512] = (unsigned short)__float_as_uint(a[k].x * a[k].x + a[k].y * a[k].y);
+        }
+#elif defined(GCWT_EXP_V2STORE)
+        {   // what-if: the same bytes as 8 stores of 8 bytes (lanes consecutive): per-request or per-byte cost?
+            float2* o2 = (float2*)(out_c + (int64_t)s_ids[s] * prm.s_stride) + rel;
+#pragma unroll
+            for (int k = 0; k < 16; k += 2)
+                if (mask & (1u << k)) o2[(k >> 1) * 256] = make_float2(a[k].x * a[k].x + a[k].y * a[k].y, a[k + 1].x * a[k + 1].x + a[k + 1].y * a[k + 1].y);
+        }
+#elif defined(GCWT_EXP_L2STORE)
+        store_column<KIND>((typename out_elem<KIND>::type*)prm.out + (blockIdx.x & 255) * 4096 + rel, 256, mask, a);   // what-if: L2-resident target
+#else
         store_column<KIND>(out_c + (int64_t)s_ids[s] * prm.s_stride + rel, 256, mask, a);
+#endif
         if (MEASURE) guard_pow_add<false>(a, mask, s_pow + (s & 1));
         // no trailing barrier: the next scale's pre-pass writes A, whose readers all passed
         // the second barrier above; its pass 1 writes ex only after the next first barrier,
@@ -1744,6 +1781,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         if (fc.wide && fc.d_table2) return true;                  // fused_wide2_kernel stores scalars when it must
         return (fc.log2u >= 3 && !fc.wide) || rows_aligned;
     };
+    cudaStream_t full_meas_stream = nullptr;      // guard: where the measured chunks of the full-spectrum class run
     auto launch_class = [&](const FastClass& fc, cudaStream_t cs, bool own_span) -> int {
         const int sp = own_span ? prof_begin(p, fc.level < 0 ? 1 : (fc.interp ? 4 : 2), cs, fc.level + 2) : -1;
         // (an interpolated class that falls back to the direct kernel is still booked as [4])
@@ -1763,13 +1801,13 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prm.pow = guard ? p->d_guard_pow : nullptr; prm.pow_stride = p->n_scales;
         // the guard measures every guard_every-th chunk of a long segment (block-uniform choice in the kernels)
         auto set_guard_sampling = [&](int64_t n_chunks, int every, double chunk_to_rate) {
-            prm.guard_every = n_chunks >= 64 ? every : 1;
+            prm.guard_every = n_chunks >= 256 ? every : (n_chunks >= 64 ? every / 2 : 1);
             const double w = (double)n_chunks / (double)((n_chunks + prm.guard_every - 1) / prm.guard_every);
             prm.pow_weight = (float)w;
             // chunk energy -> energy of the segment at the full rate: D samples per decimated one, chunks overlap
             prm.ech_weight = (float)(w * chunk_to_rate);
         };
-        set_guard_sampling(prm.n_chunks, fc.level >= 0 ? 4 : 8,
+        set_guard_sampling(prm.n_chunks, fc.level >= 0 ? 8 : 16,
                            (double)(fc.level >= 0 ? (int64_t(1) << fc.level) : 1) * (double)fc.hop / (double)fc.nc_full);
         if (fc.level >= 0 && fc.interp && fc.wide && fc.d_table2) {
             const LevelGeom& g = lv[fc.level];
@@ -1778,7 +1816,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.offset = fc.offset2; prm.hop = fc.hop2;
             prm.n_chunks = (n + fc.hop2 - 1) / fc.hop2;
             prm.table = fc.d_table2;
-            set_guard_sampling(prm.n_chunks, 4, (double)(int64_t(1) << fc.level) * (double)fc.hop2 / (double)(2 * fc.nc_full));
+            set_guard_sampling(prm.n_chunks, 8, (double)(int64_t(1) << fc.level) * (double)fc.hop2 / (double)(2 * fc.nc_full));
             prm.p_cols = 8; prm.log2p = 3; prm.units_per_chunk = 1;
             prm.iters = rows_aligned ? 1 : 0;                      // 128-bit stores allowed
             const int64_t nblk = n_channels * prm.n_chunks;
@@ -1842,7 +1880,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
                     count_launch();
                 }
                 prm.q_mode = prm.guard_every > 1 ? 1 : 0; prm.n_chunks = n_meas;
-                launch_full<TIn>(p->out_kind, (unsigned)(n_channels * prm.n_chunks), cs, prm, true);
+                launch_full<TIn>(p->out_kind, (unsigned)(n_channels * prm.n_chunks), full_meas_stream ? full_meas_stream : cs, prm, true);
             }
         }
         count_launch();
@@ -1850,7 +1888,21 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         return GCWT_OK;
     };
 
-    // full-spectrum and direct classes: one after the other on the caller's stream
+    // full-spectrum and direct classes: one after the other on the caller's stream.  With the guard on, the
+    // (few) measured chunks of the full-spectrum class run as a launch of their own on a forked stream, so that
+    // its partial last wave overlaps the main launch instead of extending it (serial when profiling per family).
+    bool side0_pending = false;
+    if (guard && !p->profile && getenv("GCWT_STREAMS") == nullptr) {
+        if (!p->side_stream[0]) {
+            GCWT_CUDA_OK(cudaStreamCreateWithFlags(&p->side_stream[0], cudaStreamNonBlocking));
+            GCWT_CUDA_OK(cudaEventCreateWithFlags(&p->ev_join[0], cudaEventDisableTiming));
+        }
+        if (!p->ev_fork) GCWT_CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+        GCWT_CUDA_OK(cudaEventRecord(p->ev_fork, st));
+        GCWT_CUDA_OK(cudaStreamWaitEvent(p->side_stream[0], p->ev_fork, 0));
+        full_meas_stream = p->side_stream[0];
+        side0_pending = true;
+    }
     int n_group = 0;
     for (const FastClass& fc : p->classes) {
         if (uses_interp(fc)) { ++n_group; continue; }
@@ -1889,8 +1941,13 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         for (int k = 0; k < n_side; ++k) {
             GCWT_CUDA_OK(cudaEventRecord(p->ev_join[k], p->side_stream[k]));
             GCWT_CUDA_OK(cudaStreamWaitEvent(st, p->ev_join[k], 0));
+            if (k == 0) side0_pending = false;
         }
         prof_end(p, sp, st);
+    }
+    if (side0_pending) {
+        GCWT_CUDA_OK(cudaEventRecord(p->ev_join[0], p->side_stream[0]));
+        GCWT_CUDA_OK(cudaStreamWaitEvent(st, p->ev_join[0], 0));
     }
     GCWT_CUDA_OK(cudaGetLastError());
     return GCWT_OK;

@@ -22,16 +22,34 @@ __global__ void mean_partial_kernel(const TIn* __restrict__ x, int64_t n, int64_
                                     double* __restrict__ partial) {
     const int c = blockIdx.y, nb = gridDim.x;
     const TIn* xc = x + (int64_t)c * stride;
-    const int64_t per = (n + nb - 1) / nb;
+    // block ranges start on multiples of 4 samples so that aligned rows can be read as 128-bit vectors
+    const int64_t per = (((n + nb - 1) / nb) + 3) & ~int64_t(3);
     const int64_t lo = (int64_t)blockIdx.x * per;
     const int64_t hi = min(n, lo + per);
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;              // independent chains: four loads in flight
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;              // independent chains: several loads in flight
     int64_t i = lo + threadIdx.x;
-    for (; i + 3 * (int64_t)blockDim.x < hi; i += 4 * (int64_t)blockDim.x) {
-        a0 += (double)xc[i];
-        a1 += (double)xc[i + blockDim.x];
-        a2 += (double)xc[i + 2 * (int64_t)blockDim.x];
-        a3 += (double)xc[i + 3 * (int64_t)blockDim.x];
+    if (sizeof(TIn) == 4 && (((uintptr_t)xc) & 15) == 0 && lo < hi) {
+        // fp32 rows: four samples per load, two loads in flight per thread (the kernel is a pure HBM read)
+        const float4* v = (const float4*)(xc + lo);
+        const int64_t nv = (hi - lo) >> 2;
+        int64_t k = threadIdx.x;
+        for (; k + blockDim.x < nv; k += 2 * (int64_t)blockDim.x) {
+            const float4 p = v[k], q = v[k + blockDim.x];
+            a0 += (double)p.x + (double)p.y; a1 += (double)p.z + (double)p.w;
+            a2 += (double)q.x + (double)q.y; a3 += (double)q.z + (double)q.w;
+        }
+        for (; k < nv; k += blockDim.x) {
+            const float4 p = v[k];
+            a0 += (double)p.x + (double)p.y; a1 += (double)p.z + (double)p.w;
+        }
+        i = lo + (nv << 2) + threadIdx.x;                        // the (< 4) samples behind the last full vector
+    } else {
+        for (; i + 3 * (int64_t)blockDim.x < hi; i += 4 * (int64_t)blockDim.x) {
+            a0 += (double)xc[i];
+            a1 += (double)xc[i + blockDim.x];
+            a2 += (double)xc[i + 2 * (int64_t)blockDim.x];
+            a3 += (double)xc[i + 3 * (int64_t)blockDim.x];
+        }
     }
     for (; i < hi; i += blockDim.x) a0 += (double)xc[i];
     const double acc = (a0 + a1) + (a2 + a3);

@@ -145,7 +145,7 @@ def run_channel_shard(plan, x_local, out=None):
     return plan.execute(x_local, out)
 
 
-def _time_shard_tiles(plan, core, rank, world, tile, emit, group=None, means=None):
+def _time_shard_tiles(plan, core, rank, world, tile, emit, group=None, means=None, lens=None):
     """Shared driver of the time-sharded transforms.  ``emit(a, b)`` returns ``(out, out_start)`` for the
     tile of core samples [a, b) and is told when the tile is complete through ``emit.done(out, a, b)``.
 
@@ -158,7 +158,9 @@ def _time_shard_tiles(plan, core, rank, world, tile, emit, group=None, means=Non
     n_ch, n_local = core.shape
     halo = required_halo(plan)
     # lengths first: an unusable partition must raise on every rank before any rank enters another collective
-    lens = gather_shard_lengths(n_local, rank, world, core.device, group)
+    # (``lens`` from an earlier call on the same partition skips the all-gather and its host synchronisation)
+    if lens is None:
+        lens = gather_shard_lengths(n_local, rank, world, core.device, group)
     check_time_shards(lens, halo)
     if means is None:
         sums = plan.channel_means(core) * float(n_local)
@@ -224,12 +226,13 @@ def run_time_shard(plan, core, rank, world, out=None, group=None, tile=None):
     return out
 
 
-def run_time_shard_tiled(plan, core, rank, world, tile, out=None, consumer=None, group=None, means=None):
+def run_time_shard_tiled(plan, core, rank, world, tile, out=None, consumer=None, group=None, means=None, lens=None):
     """As :func:`run_time_shard` for shards whose coefficients do not fit in device memory: the shard is
     transformed in time tiles into a reused (channels, scales, tile) buffer and every finished tile is
     handed to ``consumer(out, a, b)`` (core sample range [a, b); interior tiles come first, the tiles
-    next to a seam last).  Returns the number of coefficients produced on this rank."""
+    next to a seam last).  ``lens``: the shard lengths of all ranks when they are already known (e.g. from
+    :func:`gather_shard_lengths` once per partition).  Returns the number of coefficients produced on this rank."""
     tile = int(min(tile, core.shape[1]))
     if out is None:
         out = plan.alloc_out(core.shape[0], tile)
-    return _time_shard_tiles(plan, core, rank, world, tile, _Emit(lambda a, b: (out, 0), consumer), group, means)
+    return _time_shard_tiles(plan, core, rank, world, tile, _Emit(lambda a, b: (out, 0), consumer), group, means, lens)

@@ -84,3 +84,18 @@ def test_transform_pool_width_streams_only_the_bins():
         assert len(cwt.time) == got.shape[2] and abs(cwt.time[0] - 255.5 / fs) < 1e-12
     with pytest.raises(ValueError):
         ContinuousWaveletTransform(dtype=np.float32, output="complex").transform(X[0], fs=fs, pool_width=16)
+
+
+def test_pooled_host_path_with_forced_time_tiles(monkeypatch):
+    """Tiles of the pooled host path end on bin boundaries, whatever tile length is asked for."""
+    fs, n = 1000.0, 50001
+    x = synth.chirp_pink(n, fs, 7, np.float32)
+    cwt = ContinuousWaveletTransform(dtype=np.float32)
+    cwt.transform(x, fs=fs)
+    want = _np_pool(cwt.amplitude, 300, "mean")
+    monkeypatch.setenv("GCWT_HOST_TILE", "7000")
+    pooled = ContinuousWaveletTransform(dtype=np.float32)
+    pooled.transform(x, fs=fs, pool_width=300)
+    assert pooled.last_plan.host_stats()["tiles"] == -(-n // 6900)
+    rel = np.linalg.norm(pooled.amplitude - want, axis=1) / np.linalg.norm(want, axis=1)
+    assert pooled.amplitude.shape == want.shape and rel.max() <= 3e-6, rel.max()
