@@ -387,18 +387,17 @@ int generic_execute(gcwt_plan* p, const std::vector<int>& ids, const void* x, in
         return generic_run<double, double, double>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
                                                    halo_r, d_means, out, s_stride, c_stride, st);
     }
-    if (fp64_for_fp32_plan) {              // accuracy guard: fp64 arithmetic, the plan's fp32 output
-        if (in_type == GCWT_F32)
-            return generic_run<float, double, float>(p, ids, (const float*)x, n_channels, n_samples, x_stride, halo_l,
-                                                     halo_r, d_means, out, s_stride, c_stride, st);
-        return generic_run<double, double, float>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
-                                                  halo_r, d_means, out, s_stride, c_stride, st);
-    }
+    // fp32 plans: the scales the fused kernels cannot take (wavelets whose truncated kernels are genuinely
+    // broadband, GCWT_FLAG_FORCE_GENERIC) and the pairs the accuracy guard re-computes.  Always fp64 arithmetic
+    // with an fp32 store: a full-spectrum fp32 transform has no guard of its own against recordings whose
+    // energy sits far from a scale's band (errors of 1e-4 ... 1e-3 there), and since round 2 the fp64
+    // four-step path is the faster one anyway.
+    (void)fp64_for_fp32_plan;
     if (in_type == GCWT_F32)
-        return generic_run<float, float, float>(p, ids, (const float*)x, n_channels, n_samples, x_stride, halo_l,
-                                                halo_r, d_means, out, s_stride, c_stride, st);
-    return generic_run<double, float, float>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
-                                             halo_r, d_means, out, s_stride, c_stride, st);
+        return generic_run<float, double, float>(p, ids, (const float*)x, n_channels, n_samples, x_stride, halo_l,
+                                                 halo_r, d_means, out, s_stride, c_stride, st);
+    return generic_run<double, double, float>(p, ids, (const double*)x, n_channels, n_samples, x_stride, halo_l,
+                                              halo_r, d_means, out, s_stride, c_stride, st);
 }
 
 // ----------------------------------------------------------------------------- probe

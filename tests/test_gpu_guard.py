@@ -149,3 +149,19 @@ def test_cfg3_grid_full_128_scales_against_oracle():
     err = _l2rel(cwt.power.astype(np.float64), amp ** 2)
     assert err.max() <= FP32_BAR, (int(np.argmax(err)), err.max(), int(lev[int(np.argmax(err))]))
     assert cwt.last_plan.guard_stats()["last"] == 0
+
+
+@pytest.mark.parametrize("gamma,beta", [(9, 10), (3, 5), (6, 1)])
+def test_broadband_wavelets_on_hostile_spectra(gamma, beta):
+    """Wavelets whose truncated kernels are genuinely broadband have scales no fused kernel takes (level -2).
+    In an fp32 plan those are computed in fp64 arithmetic (an fp32 full-spectrum transform would miss the
+    bar by 1e-4 ... 1e-3 on this input); found by tools/fuzz_fp32_vs_fp64.py with FUZZ_HOSTILE=1."""
+    fs, n = 1000.0, 40000
+    x = _hostile("white_hp", n, fs, seed=2).astype(np.float32)
+    amp, f, _ = orc.cwt_amplitude(x.astype(np.float64), fs, gamma=gamma, beta=beta, voices_per_octave=8, parallel=True)
+    cwt = ContinuousWaveletTransform(wavelet=Morse(gamma=gamma, beta=beta), dtype=np.float32)
+    cwt.transform(x, fs=fs, voices_per_octave=8)
+    assert cwt.frequencies.tolist() == f.tolist()
+    assert (cwt.last_plan.levels() == -2).any()
+    err = _l2rel(cwt.amplitude.astype(np.float64), amp)
+    assert err.max() <= FP32_BAR, (gamma, beta, int(np.argmax(err)), err.max())

@@ -24,8 +24,25 @@ for case in range(n_cases):
     nch = int(rng.choice([1, 1, 2, 5]))
     vpo = int(rng.choice([4, 8, 10, 16]))
     output = str(rng.choice(["amplitude", "power", "complex"]))
-    x = rng.standard_normal((nch, n)).astype(np.float32).cumsum(axis=1) * 0.05 + rng.standard_normal((nch, n)).astype(np.float32) \
-        + float(rng.uniform(-3, 3))
+    kind = str(rng.choice(["walk", "walk", "tilt", "tilt", "highpass", "tones"])) if os.environ.get("FUZZ_HOSTILE") else "walk"
+    if kind == "walk":
+        x = rng.standard_normal((nch, n)).astype(np.float32).cumsum(axis=1) * 0.05 + rng.standard_normal((nch, n)).astype(np.float32) \
+            + float(rng.uniform(-3, 3))
+    else:
+        spec = np.fft.rfft(rng.standard_normal((nch, n)), axis=1)
+        fr = np.fft.rfftfreq(n, 1.0 / fs)
+        if kind == "tilt":
+            g = (np.maximum(fr, fr[1] if n > 2 else 1.0) / fr[-1]) ** float(rng.uniform(-1.5, 4.0))
+        elif kind == "highpass":
+            g = (fr >= float(rng.uniform(0.01, 0.4)) * fs / 2).astype(float)
+        else:
+            g = np.full_like(fr, float(10 ** rng.uniform(-4, -1)))
+        x = np.fft.irfft(spec * g, n=n, axis=1)
+        if kind == "tones":
+            t = np.arange(n) / fs
+            x = x + np.sin(2 * np.pi * float(rng.uniform(0.05, 0.45)) * fs * t) \
+                + float(10 ** rng.uniform(-4, -1)) * np.sin(2 * np.pi * float(rng.uniform(0.001, 0.02)) * fs * t)
+        x = (x / max(x.std(), 1e-30) + float(rng.uniform(-3, 3))).astype(np.float32)
     ts = None
     if n >= 4097 and rng.random() < 0.4:                       # a gap -> two epochs
         ts = np.arange(n) / fs
@@ -63,9 +80,10 @@ for case in range(n_cases):
     tag = "ok " if err <= bar else "BAD"
     if err > bar:
         fails.append((case, gamma, beta, fs, n, nch, vpo, output, err))
-    print("case %2d %s g=%g b=%g fs=%g n=%d ch=%d vpo=%d %s epochs=%d S=%d levels=%s err=%.2e" % (
-        case, tag, gamma, beta, fs, n, nch, vpo, output, 2 if ts is not None else 1, a.shape[1],
-        sorted(set(lev.tolist())), err), flush=True)
+    rer = cwt.last_plan.guard_stats()["last"] if cwt.last_plan is not None else -1
+    print("case %2d %s %-8s g=%g b=%g fs=%g n=%d ch=%d vpo=%d %s epochs=%d S=%d levels=%s err=%.2e recomputed=%d" % (
+        case, tag, kind, gamma, beta, fs, n, nch, vpo, output, 2 if ts is not None else 1, a.shape[1],
+        sorted(set(lev.tolist())), err, rer), flush=True)
     if err > 0.5 * bar:
         order = np.argsort(rel.max(axis=0))[::-1][:6]
         print("      worst scales (index, level, L, err): " + ", ".join(
