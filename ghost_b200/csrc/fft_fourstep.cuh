@@ -1,6 +1,6 @@
 // fp64 overlap-save through a four-step FFT whose sub-transforms run in shared memory.
 //
-// An n-point transform (n = N1 * N2 = 2^10 ... 2^20, N1, N2 <= 1024) is two kernels instead of one launch
+// An n-point transform (n = N1 * N2 = 2^11 ... 2^20, N1, N2 <= 1024) is two kernels instead of one launch
 // per radix pass: transforms of length N1 down the columns of the N1 x N2 matrix, a twiddle, transforms of
 // length N2 along the rows.  The forward transform leaves the spectrum in "transposed" order (bin
 // k1 + N1 k2 at position k1 N2 + k2); the filter responses are tabulated in that order and the inverse
@@ -24,7 +24,8 @@ struct FourStep {
     int n1 = 0, n2 = 0;
     int rows_per_block = 0;          // kTile / N2
     int cols_per_block = 0;          // kTile / N1
-    static bool usable(int64_t n) { return n >= 1024 && n <= (int64_t(1) << 20) && (n & (n - 1)) == 0; }
+    // (a block tile of kTile elements must not exceed the transform: at n = 1024 it would hold two of them)
+    static bool usable(int64_t n) { return n >= kTile && n <= (int64_t(1) << 20) && (n & (n - 1)) == 0; }
     explicit FourStep(int64_t n) {
         p = ilog2_ceil(n);
         p1 = p / 2; p2 = p - p1;

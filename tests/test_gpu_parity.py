@@ -449,3 +449,17 @@ def test_multi_stream_class_launches_are_bit_identical(monkeypatch):
         cwt.transform(X, fs=fs, multichannel=True, freq_limits=[1, 400])
         outs.append(cwt.power.copy())
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("n", [700, 1000, 1500, 2047, 3000])
+def test_fp64_small_transform_sizes(n):
+    """Transform sizes around the lower limit of the four-step path (2048 points: below it the older
+    global-memory passes run).  Found by tools/fuzz_fp64_vs_oracle.py: 1024 points once had an empty grid."""
+    fs = 200.0
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) + 0.3
+    W, f, _ = orc.cwt_complex(x, fs, voices_per_octave=8, parallel=True)
+    cwt = ContinuousWaveletTransform(output="complex")
+    cwt.transform(x, fs=fs, voices_per_octave=8)
+    assert cwt.frequencies.tolist() == f.tolist() and len(f) > 0
+    assert _maxrel(cwt.coefficients, W).max() <= FP64_BAR
