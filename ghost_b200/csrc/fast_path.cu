@@ -1574,6 +1574,12 @@ __device__ __forceinline__ void full_scale_loop(const FusedParams& prm, const fl
             for (int k = 0; k < 16; k += 2)
                 if (mask & (1u << k)) o2[(k >> 1) * 256] = make_float2(a[k].x * a[k].x + a[k].y * a[k].y, a[k + 1].x * a[k + 1].x + a[k + 1].y * a[k + 1].y);
         }
+#elif defined(GCWT_EXP_STSSTORE)
+        {   // what-if: the 16 results go to shared memory instead (as a TMA bulk store would need); Yf is clobbered
+            float* stage = (float*)const_cast<float2*>(Yf);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) stage[k * 256 + rel] = sqrt_approx(a[k].x * a[k].x + a[k].y * a[k].y);
+        }
 #elif defined(GCWT_EXP_L2STORE)
         store_column<KIND>((typename out_elem<KIND>::type*)prm.out + (blockIdx.x & 255) * 4096 + rel, 256, mask, a);   // what-if: L2-resident target
 #else
