@@ -1185,6 +1185,91 @@ __device__ __forceinline__ void interp_rows_wide(const float* __restrict__ pc, f
     }
 }
 
+// 256-bit store (sm_100: STG.E.256): eight consecutive floats, 32-byte aligned
+__device__ __forceinline__ void st_v8(float* p, const float* o) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+}
+
+// The same with two adjacent coarse intervals per thread: their windows overlap in all but one sample, so the
+// 14 samples arrive as seven 64-bit shared loads (0.22 loads per output at U = 4 instead of 0.75 32-bit ones,
+// 42 % fewer shared-memory wavefronts) and the 2 U outputs leave as 256-bit stores when the rows allow it.
+// `align`: 0 rows unaligned (scalar stores), 1 16-byte aligned rows, 2 32-byte aligned rows.
+template <int KIND, int LU>
+__device__ __forceinline__ void interp_rows_wide_pairs(const float* __restrict__ pc, float* __restrict__ row,
+                                                       int ia, int ib, int own_hi, int align) {
+    constexpr int U = 1 << LU;
+    constexpr int COFF = (LU == 2) ? 0 : 4 * kWideT;
+    static_assert(kWideT == 12, "window indexing below assumes 12 taps");
+    for (int iota = ia + 2 * (int)threadIdx.x; iota < ib; iota += 512) {        // ia is even (offsets are multiples of 16)
+        float w[14];                                                            // pc[iota - 6 .. iota + 7]
+        const float2* p2 = (const float2*)(pc + iota - 6);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) { const float2 t = p2[j]; w[2 * j] = t.x; w[2 * j + 1] = t.y; }
+        float o[2 * U];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                                           // interval iota + h: window w[1 + h .. 12 + h]
+            o[h * U] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_approx(w[6 + h]) : w[6 + h];
+#pragma unroll
+            for (int phi = 1; phi < U; ++phi) {
+                float acc = c_interp_wide[COFF + phi * kWideT] * w[1 + h];
+#pragma unroll
+                for (int j = 1; j < kWideT; ++j) acc = fmaf(c_interp_wide[COFF + phi * kWideT + j], w[1 + h + j], acc);
+                o[h * U + phi] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_abs_approx(acc) : fmaxf(acc, 0.f);
+            }
+        }
+        float* op = row + (int64_t)iota * U;
+        if (align && (iota + 2) * U <= own_hi) {
+            if (align == 2) {
+#pragma unroll
+                for (int v = 0; v < 2 * U / 8; ++v) st_v8(op + 8 * v, o + 8 * v);
+            } else {
+#pragma unroll
+                for (int v = 0; v < 2 * U / 4; ++v) ((float4*)op)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2 * U; ++i) if (iota * U + i < own_hi) op[i] = o[i];
+        }
+    }
+}
+
+// U = 8 on the grid U = D/2 (level 4): two adjacent intervals per thread, kInterpT = 8 taps from the constant bank
+// (the U <= 8 designs at over-sampling 4), the 10 window samples as five 64-bit shared loads, the 16 outputs as
+// two 256-bit stores (0.31 loads and 0.125 stores per output against 1 and 1 in the sliding form).
+template <int KIND>
+__device__ __forceinline__ void interp_rows_pairs8(const float* __restrict__ pc, float* __restrict__ row,
+                                                   int ia, int ib, int own_hi, int align) {
+    constexpr int U = 8, COFF = 6 * kInterpT;
+    static_assert(kInterpT == 8, "window indexing below assumes 8 taps");
+    for (int iota = ia + 2 * (int)threadIdx.x; iota < ib; iota += 512) {        // ia is even
+        float w[10];                                                            // pc[iota - 4 .. iota + 5]
+        const float2* p2 = (const float2*)(pc + iota - 4);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { const float2 t = p2[j]; w[2 * j] = t.x; w[2 * j + 1] = t.y; }
+        float o[2 * U];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                                           // interval iota + h: window w[1 + h .. 8 + h]
+            o[h * U] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_approx(w[4 + h]) : w[4 + h];
+#pragma unroll
+            for (int phi = 1; phi < U; ++phi) {
+                float acc = c_interp_small[COFF + phi * kInterpT] * w[1 + h];
+#pragma unroll
+                for (int j = 1; j < kInterpT; ++j) acc = fmaf(c_interp_small[COFF + phi * kInterpT + j], w[1 + h + j], acc);
+                o[h * U + phi] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_abs_approx(acc) : fmaxf(acc, 0.f);
+            }
+        }
+        float* op = row + (int64_t)iota * U;
+        if (align == 2 && (iota + 2) * U <= own_hi) {
+            st_v8(op, o);
+            st_v8(op + 8, o + 8);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2 * U; ++i) if (iota * U + i < own_hi) op[i] = o[i];
+        }
+    }
+}
+
 template <int KIND, bool GUARD>
 __global__ void __launch_bounds__(256, GCWT_INTERP_CTAS)
 fused_interp_kernel(const FusedParams prm) {
@@ -1308,7 +1393,14 @@ fused_interp_kernel(const FusedParams prm) {
                 interp_rows_small<KIND, 1>(pcs, row, ia, ib, own_hi);
             } else {
                 switch (lu) {
+#ifdef GCWT_L4_SLIDING
                     case 3:  interp_rows<KIND, 3, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
+#else
+                    case 3:
+                        if (prm.iters == 2 && prm.units_per_chunk == 1) interp_rows_pairs8<KIND>(pcs, row, ia, ib, own_hi, 2);
+                        else interp_rows<KIND, 3, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi);
+                        break;
+#endif
                     case 4:  interp_rows<KIND, 4, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
                     case 5:  interp_rows<KIND, 5, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
                     case 6:  interp_rows<KIND, 6, kInterpT>(pcs, row, prm.coef, c0, lu, ia, ib, own_hi); break;
@@ -1420,6 +1512,7 @@ fused_wide2_kernel(const FusedParams prm) {
     for (int k = 0; k < 8; ++k) tw2k[k] = tw_pos(prm.twf, 2 * tid * k);        // e^{2 pi i m' k / 2048}
     float* const out_c = (float*)prm.out + c * prm.c_stride + t0;
     const bool aligned = prm.iters != 0;                           // rows 16-byte aligned: 128-bit stores allowed
+    const int align = prm.iters;                                   // 2: 32-byte aligned rows (256-bit stores)
     float2* const A = B1;
     float2* const ex = B0;
     float* const Pc = (float*)B1;
@@ -1479,8 +1572,14 @@ fused_wide2_kernel(const FusedParams prm) {
         for (int sl = 0; sl < 2 && pair + sl < prm.n_scales; ++sl) {
             const float* pcs = Pc + sl * kPcStride;
             float* row = out_c + (int64_t)s_ids[pair + sl] * prm.s_stride;
+#ifdef GCWT_WIDE_SINGLE
             if (lu == 2) interp_rows_wide<KIND, 2>(pcs, row, ia, ib, own_hi, aligned);
             else interp_rows_wide<KIND, 3>(pcs, row, ia, ib, own_hi, aligned);
+#else
+            (void)aligned;
+            if (lu == 2) interp_rows_wide_pairs<KIND, 2>(pcs, row, ia, ib, own_hi, align);
+            else interp_rows_wide_pairs<KIND, 3>(pcs, row, ia, ib, own_hi, align);
+#endif
         }
         __syncthreads();
     }
@@ -1782,6 +1881,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
     // the thread <-> interval interpolators of fused_interp_kernel (U = 2, 4) write 128-bit vectors:
     // rows must be 16-byte aligned, else the class falls back to the direct kernel
     const bool rows_aligned = ((uintptr_t)out % 16 == 0) && (s_stride % 4 == 0) && (c_stride % 4 == 0);
+    const bool rows_aligned32 = ((uintptr_t)out % 32 == 0) && (s_stride % 8 == 0) && (c_stride % 8 == 0);
     auto uses_interp = [&](const FastClass& fc) {
         if (fc.level < 0 || !fc.interp) return false;
         if (fc.wide && fc.d_table2) return true;                  // fused_wide2_kernel stores scalars when it must
@@ -1824,7 +1924,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.table = fc.d_table2;
             set_guard_sampling(prm.n_chunks, 8, (double)(int64_t(1) << fc.level) * (double)fc.hop2 / (double)(2 * fc.nc_full));
             prm.p_cols = 8; prm.log2p = 3; prm.units_per_chunk = 1;
-            prm.iters = rows_aligned ? 1 : 0;                      // 128-bit stores allowed
+            prm.iters = rows_aligned32 ? 2 : (rows_aligned ? 1 : 0);   // 256-bit / 128-bit stores allowed
             const int64_t nblk = n_channels * prm.n_chunks;
             if (nblk > 0x7fffffffLL) { set_error("fast path: grid too large"); return GCWT_ERR_UNSUPPORTED; }
             if (p->out_kind == GCWT_OUT_AMPLITUDE) {
@@ -1840,7 +1940,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
             prm.log2d = fc.level;
             prm.p_cols = (int)(fc.nc_full / kBins);
             prm.log2p = ilog2_ceil(prm.p_cols);
-            prm.iters = 1;
+            prm.iters = rows_aligned32 ? 2 : 1;                    // 2: rows 32-byte aligned (256-bit stores allowed)
             // enough blocks for ~6 waves of 2 x 148, but at least ~64 coarse intervals per block
             const int64_t chunks = n_channels * prm.n_chunks;
             int64_t splits = (1776 + chunks - 1) / chunks;
