@@ -1195,20 +1195,21 @@ __device__ __forceinline__ void st_v8(float* p, const float* o) {
 // 14 samples arrive as seven 64-bit shared loads (0.22 loads per output at U = 4 instead of 0.75 32-bit ones,
 // 42 % fewer shared-memory wavefronts) and the 2 U outputs leave as 256-bit stores when the rows allow it.
 // `align`: 0 rows unaligned (scalar stores), 1 16-byte aligned rows, 2 32-byte aligned rows.
-template <int KIND, int LU>
+template <int KIND, int LU, int NI>       // NI adjacent coarse intervals per thread (ia must be a multiple of NI, NI even)
 __device__ __forceinline__ void interp_rows_wide_pairs(const float* __restrict__ pc, float* __restrict__ row,
                                                        int ia, int ib, int own_hi, int align) {
     constexpr int U = 1 << LU;
     constexpr int COFF = (LU == 2) ? 0 : 4 * kWideT;
-    static_assert(kWideT == 12, "window indexing below assumes 12 taps");
-    for (int iota = ia + 2 * (int)threadIdx.x; iota < ib; iota += 512) {        // ia is even (offsets are multiples of 16)
-        float w[14];                                                            // pc[iota - 6 .. iota + 7]
+    constexpr int NW = kWideT + NI;                                             // window pc[iota - 6 .. iota + NI + 5], 64-bit aligned
+    static_assert(kWideT == 12 && NI % 2 == 0 && (NI * U) % 8 == 0, "window indexing below assumes 12 taps");
+    for (int iota = ia + NI * (int)threadIdx.x; iota < ib; iota += NI * 256) {
+        float w[NW];
         const float2* p2 = (const float2*)(pc + iota - 6);
 #pragma unroll
-        for (int j = 0; j < 7; ++j) { const float2 t = p2[j]; w[2 * j] = t.x; w[2 * j + 1] = t.y; }
-        float o[2 * U];
+        for (int j = 0; j < NW / 2; ++j) { const float2 t = p2[j]; w[2 * j] = t.x; w[2 * j + 1] = t.y; }
+        float o[NI * U];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {                                           // interval iota + h: window w[1 + h .. 12 + h]
+        for (int h = 0; h < NI; ++h) {                                          // interval iota + h: window w[1 + h .. 12 + h]
             o[h * U] = (KIND == GCWT_OUT_AMPLITUDE) ? sqrt_approx(w[6 + h]) : w[6 + h];
 #pragma unroll
             for (int phi = 1; phi < U; ++phi) {
@@ -1219,17 +1220,17 @@ __device__ __forceinline__ void interp_rows_wide_pairs(const float* __restrict__
             }
         }
         float* op = row + (int64_t)iota * U;
-        if (align && (iota + 2) * U <= own_hi) {
+        if (align && (iota + NI) * U <= own_hi) {
             if (align == 2) {
 #pragma unroll
-                for (int v = 0; v < 2 * U / 8; ++v) st_v8(op + 8 * v, o + 8 * v);
+                for (int v = 0; v < NI * U / 8; ++v) st_v8(op + 8 * v, o + 8 * v);
             } else {
 #pragma unroll
-                for (int v = 0; v < 2 * U / 4; ++v) ((float4*)op)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+                for (int v = 0; v < NI * U / 4; ++v) ((float4*)op)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 2 * U; ++i) if (iota * U + i < own_hi) op[i] = o[i];
+            for (int i = 0; i < NI * U; ++i) if (iota * U + i < own_hi) op[i] = o[i];
         }
     }
 }
@@ -1577,8 +1578,9 @@ fused_wide2_kernel(const FusedParams prm) {
             else interp_rows_wide<KIND, 3>(pcs, row, ia, ib, own_hi, aligned);
 #else
             (void)aligned;
-            if (lu == 2) interp_rows_wide_pairs<KIND, 2>(pcs, row, ia, ib, own_hi, align);
-            else interp_rows_wide_pairs<KIND, 3>(pcs, row, ia, ib, own_hi, align);
+            // (four intervals per thread at U = 4 measured slower: 1.99 vs 1.88 ms on level 2 of config 2)
+            if (lu == 2) interp_rows_wide_pairs<KIND, 2, 2>(pcs, row, ia, ib, own_hi, align);
+            else interp_rows_wide_pairs<KIND, 3, 2>(pcs, row, ia, ib, own_hi, align);
 #endif
         }
         __syncthreads();
