@@ -46,13 +46,14 @@ WORKLOADS = {
                  desc="1ch x 1kHz x 60s, 84 scales, fp32 amplitude"),
     # config 3 of BASELINE.json is 256 channels over 8 GPUs = 32 channels per GPU; its result (295 GB
     # per GPU) exceeds HBM, so it is produced in time tiles into a reused buffer (tile = samples per tile)
+    # (tile sweep on one shard: 2.25 M samples 91.3 ms, 4.5 M 88.8 ms, 6 M 89.0 ms; 4.5 M = a 74 GB tile buffer)
     "cfg3": dict(fs=30000.0, n=18000000, channels=32, freq_limits=[1.7, 15000.0], vpo=10, output="power",
-                 tile=2250000, desc="32ch/GPU x 30kHz x 10min, 128 scales, fp32 power, streamed in 8 time tiles"),
+                 tile=4500000, desc="32ch/GPU x 30kHz x 10min, 128 scales, fp32 power, streamed in 4 time tiles"),
     # config 4 of BASELINE.json: one 24 h recording at 30 kHz (2.592e9 samples) time-sharded over 8 GPUs
     # = 3.24e8 samples per GPU; every step does the mean all-reduce, the NCCL halo exchange with both
     # neighbours and the tiled transform of the shard
     "cfg4": dict(fs=30000.0, n=324000000, channels=1, freq_limits=[1.7, 15000.0], vpo=10, output="power",
-                 tile=36000000, time_shard=True, plan_n=2592000000,
+                 tile=108000000, time_shard=True, plan_n=2592000000,      # (36 M: 52.2 ms per shard, 81 M: 50.4, 108 M: 49.8)
                  desc="1ch x 30kHz, 3.24e8 samples per GPU (24 h over 8 GPUs), 128 scales, fp32 power, "
                       "time-sharded with NCCL halos, streamed in time tiles"),
     # config 5 of BASELINE.json is the fp64 complex parity sweep; this is its largest single shape as a
@@ -606,7 +607,7 @@ def run_extra(args, dev, local, rank, world, peak):
         coeffs = 256.0 * wl["n"] * len(freqs)
         gbs = 256.0 * wl["n"] * (len(freqs) * 4 + 4) / (ms * 1e-3) / 1e9
         extra["cfg3_full"] = {"workload": "cfg3: 256ch x 30kHz x 10min x 128 scales, fp32 power, 32 channels per GPU, results "
-                                          "streamed in 8 time tiles per GPU", "scaling": "channel-shard x8", "ms_per_step": ms,
+                                          "streamed in %d time tiles per GPU" % (-(-wl["n"] // wl["tile"])), "scaling": "channel-shard x8", "ms_per_step": ms,
                               "value": coeffs / (ms * 1e-3), "unit": UNIT, "achieved_gbs": gbs,
                               "hbm_frac_of_measured_aggregate": gbs / (peak * 8), "hbm_frac_of_nominal_8TBs": gbs / 64000.0,
                               "guard_pairs_recomputed_fp64": plan.guard_stats()["total"]}
