@@ -202,7 +202,11 @@ int host_execute(gcwt_plan* p, const void* x, int in_type, int64_t n_channels, i
                        h.h_pool[b] + ((size_t)c * S + s) * bins_per_tile, (size_t)nb * sizeof(double));
     };
     Pending pend[2];
-    std::thread copier[2];
+    struct Copiers {                                               // joined on every return path (an early error return
+        std::thread t[2];                                          // must not destroy a running thread)
+        ~Copiers() { for (auto& th : t) if (th.joinable()) th.join(); }
+        std::thread& operator[](int i) { return t[i]; }
+    } copier;
     auto finish = [&](int b) -> int {                              // tile in slot b has reached the caller's array
         if (!pend[b].live) return GCWT_OK;
         if (pooled) {
