@@ -626,7 +626,10 @@ def run_extra(args, dev, local, rank, world, peak):
     blk = synth_channels(wl, 1, 1 << 24, 0, pin=False)[0].numpy()
     # every rank cuts ITS samples out of the same periodic recording (a 2^24-sample chirp + pink block repeated)
     idx0 = lo % blk.size
-    x = torch.from_numpy(np.concatenate([blk[idx0:], np.tile(blk, (n_local + blk.size - 1) // blk.size + 1)])[:n_local].copy()).to(dev)[None, :]
+    # the shard is stored with room for its halos (sharding.TimeShard): the neighbours' samples are received in place
+    shard = sharding.TimeShard(1, n_local, halo, dtype=torch.float32, device=dev)
+    shard.core.copy_(torch.from_numpy(np.concatenate([blk[idx0:], np.tile(blk, (n_local + blk.size - 1) // blk.size + 1)])[:n_local].copy())[None, :])
+    x = shard.core
     tile = int(wl["tile"])
     out = plan.alloc_out(1, tile)
     M = 20000                                                   # seam check: M samples either side of the rank 0 | rank 1 seam
@@ -643,9 +646,9 @@ def run_extra(args, dev, local, rank, world, peak):
             if hi_ > lo_:
                 keep["head"][:, lo_:hi_] = o[0, :, lo_ - a:hi_ - a]
 
-    done = sharding.run_time_shard_tiled(plan, x, rank, world, tile, out=out, consumer=consumer)
+    done = sharding.run_time_shard_tiled(plan, shard, rank, world, tile, out=out, consumer=consumer)
     lens = sharding.gather_shard_lengths(n_local, rank, world, dev)          # the partition is fixed: gathered once
-    ms = timer.run(lambda: sharding.run_time_shard_tiled(plan, x, rank, world, tile, out=out, lens=lens), 3, 1)
+    ms = timer.run(lambda: sharding.run_time_shard_tiled(plan, shard, rank, world, tile, out=out, lens=lens), 3, 1)
     # the same shard with no neighbours (no collectives, zero padding at the seams): what the exchange costs
     ms_alone = timer.run(lambda: plan.execute_tiled(x, tile, out=out), 3, 1)      # (its own mean kernel included)
     # seam check on rank 0: the window [seam - halo - M, seam + halo + M) transformed unsharded

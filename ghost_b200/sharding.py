@@ -20,7 +20,7 @@ import numpy as np
 
 __all__ = ["channel_block", "time_block", "global_means", "exchange_halos", "run_channel_shard",
            "run_time_shard", "run_time_shard_tiled", "required_halo", "HaloExchange", "check_time_shards",
-           "gather_shard_lengths"]
+           "gather_shard_lengths", "TimeShard"]
 
 
 def _dist():
@@ -91,6 +91,20 @@ def check_time_shards(lens, halo):
                                  r, r + 1, lens[r], lens[r + 1], halo))
 
 
+class TimeShard:
+    """A rank's time shard stored with room for its halos: ``buf`` is (channels, halo + n_local + halo) and
+    ``core`` the view of the n_local samples this rank owns.  Fill ``core`` (e.g. ``shard.core.copy_(...)``);
+    the transforms below then receive the neighbours' halos straight into the margins, so the tiles next to a
+    seam are transformed in place -- no edge buffers, no copies of the shard."""
+
+    def __init__(self, n_channels, n_local, halo, dtype=None, device=None):
+        import torch
+        self.halo, self.n_local = int(halo), int(n_local)
+        self.buf = torch.zeros((int(n_channels), self.n_local + 2 * self.halo),
+                               dtype=torch.float32 if dtype is None else dtype, device=device)
+        self.core = self.buf[:, self.halo:self.halo + self.n_local]
+
+
 class HaloExchange:
     """The halo send / receive pairs with both neighbours, posted at construction and completed by
     ``wait()`` -- so that the tiles which need no neighbour data can be transformed in between.
@@ -99,13 +113,14 @@ class HaloExchange:
     rank - 1 and the first ``halo`` samples of rank + 1, or None at the true ends of the recording
     (which the kernels zero-pad, like the reference)."""
 
-    def __init__(self, core, halo, rank, world, group=None):
+    def __init__(self, core, halo, rank, world, group=None, into=None):
         import torch
         dist = _dist()
         n_ch, n_local = core.shape
         self.left = self.right = None
         self._reqs = []
         self._keep = []
+        self._into = into                    # a TimeShard: wait() moves the received halos into its margins
         ops = []
         if halo > 0 and rank < world - 1:
             tail = core[:, n_local - halo:].contiguous()
@@ -124,6 +139,13 @@ class HaloExchange:
         for req in self._reqs:
             req.wait()
         self._reqs = []
+        if self._into is not None:           # halo-sized copies (<= 1 MB per channel) into the shard's own margins
+            sh = self._into
+            if self.left is not None:
+                sh.buf[:, :sh.halo].copy_(self.left)
+            if self.right is not None:
+                sh.buf[:, sh.halo + sh.n_local:].copy_(self.right)
+            self._into = None
         return self.left, self.right
 
 
@@ -155,8 +177,13 @@ def _time_shard_tiles(plan, core, rank, world, tile, emit, group=None, means=Non
     transformed while it is in flight; the tiles next to a seam follow from small edge buffers
     (halo + tile samples), so the shard itself is never copied."""
     import torch
+    shard = core if isinstance(core, TimeShard) else None
+    if shard is not None:
+        core = shard.core
     n_ch, n_local = core.shape
     halo = required_halo(plan)
+    if shard is not None and shard.halo < halo:
+        raise ValueError("TimeShard was made with a halo of {} samples but this plan needs {}".format(shard.halo, halo))
     # lengths first: an unusable partition must raise on every rank before any rank enters another collective
     # (``lens`` from an earlier call on the same partition skips the all-gather and its host synchronisation)
     if lens is None:
@@ -165,7 +192,7 @@ def _time_shard_tiles(plan, core, rank, world, tile, emit, group=None, means=Non
     if means is None:
         sums = plan.channel_means(core) * float(n_local)
         means = global_means(sums, n_local, group)
-    xch = HaloExchange(core, halo, rank, world, group)
+    xch = HaloExchange(core, halo, rank, world, group, into=shard)
     has_l, has_r = rank > 0 and halo > 0, rank < world - 1 and halo > 0
     tile = int(min(tile, n_local))
     tiles = [(a, min(n_local, a + tile)) for a in range(0, n_local, tile)]
@@ -182,6 +209,16 @@ def _time_shard_tiles(plan, core, rank, world, tile, emit, group=None, means=Non
         done += (b - a) * n_ch * plan.n_scales
     left, right = xch.wait()
     for a, b in edge:
+        if shard is not None:
+            # the halos sit in the shard's own margins: transform the tile where it is
+            o = shard.halo                                        # index of core sample 0 in shard.buf
+            hl = min(halo, a + (halo if has_l else 0))
+            hr = min(halo, n_local - b + (halo if has_r else 0))
+            out, o0 = emit(a, b)
+            plan.execute(shard.buf, out, means=means, start=o + a, stop=o + b, halo_left=hl, halo_right=hr, out_start=o0)
+            emit.done(out, a, b)
+            done += (b - a) * n_ch * plan.n_scales
+            continue
         # [left halo | core[lo:hi] | right halo]: only as much of the core as this tile can reach
         lo, hi = max(0, a - halo), min(n_local, b + halo)
         parts, off = [], 0
@@ -216,12 +253,14 @@ class _Emit:
 
 
 def run_time_shard(plan, core, rank, world, out=None, group=None, tile=None):
-    """Time-sharded transform of this rank's ``core`` (channels, n_local) CUDA tensor.
+    """Time-sharded transform of this rank's ``core`` (channels, n_local) CUDA tensor, or of a
+    :class:`TimeShard` (halos received in place, no edge buffers).
 
     Returns the (channels, scales, n_local) coefficients of the core samples (they stay sharded)."""
-    n_local = core.shape[1]
+    inner = core.core if isinstance(core, TimeShard) else core
+    n_local = inner.shape[1]
     if out is None:
-        out = plan.alloc_out(core.shape[0], n_local)
+        out = plan.alloc_out(inner.shape[0], n_local)
     _time_shard_tiles(plan, core, rank, world, n_local if tile is None else tile, _Emit(lambda a, b: (out, a)), group)
     return out
 
@@ -232,7 +271,8 @@ def run_time_shard_tiled(plan, core, rank, world, tile, out=None, consumer=None,
     handed to ``consumer(out, a, b)`` (core sample range [a, b); interior tiles come first, the tiles
     next to a seam last).  ``lens``: the shard lengths of all ranks when they are already known (e.g. from
     :func:`gather_shard_lengths` once per partition).  Returns the number of coefficients produced on this rank."""
-    tile = int(min(tile, core.shape[1]))
+    inner = core.core if isinstance(core, TimeShard) else core
+    tile = int(min(tile, inner.shape[1]))
     if out is None:
-        out = plan.alloc_out(core.shape[0], tile)
+        out = plan.alloc_out(inner.shape[0], tile)
     return _time_shard_tiles(plan, core, rank, world, tile, _Emit(lambda a, b: (out, 0), consumer), group, means, lens)

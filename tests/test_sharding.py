@@ -113,7 +113,7 @@ def test_partition_helpers():
     assert all(a[1] == b[0] and a[1] % 16384 == 0 for a, b in zip(blocks[:-1], blocks[1:]))
 
 
-def _worker_tiled(rank, world, port, n, ntaps, tile, ret):
+def _worker_tiled(rank, world, port, n, ntaps, tile, ret, in_place=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -124,6 +124,10 @@ def _worker_tiled(rank, world, port, n, ntaps, tile, ret):
         plan = FakePlan(taps)
         lo, hi = sharding.time_block(n, rank, world, align=8)
         core = torch.from_numpy(x[:, lo:hi].copy())
+        if in_place:                                   # the shard keeps room for its halos: they are received in place
+            shard = sharding.TimeShard(2, hi - lo, sharding.required_halo(plan), dtype=torch.float64)
+            shard.core.copy_(core)
+            core = shard
         got = torch.zeros((2, 1, hi - lo), dtype=torch.complex128)
         order = []
 
@@ -139,13 +143,14 @@ def _worker_tiled(rank, world, port, n, ntaps, tile, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("in_place", [False, True])
 @pytest.mark.parametrize("world,n,ntaps,tile", [(2, 6000, 301, 500), (3, 9000, 257, 1000), (2, 4000, 129, 4000)])
-def test_time_shard_tiles_overlap_the_exchange(world, n, ntaps, tile):
+def test_time_shard_tiles_overlap_the_exchange(world, n, ntaps, tile, in_place):
     """Tiled time shards: interior tiles are transformed while the halos travel, the tiles next to a seam
     afterwards from small edge buffers; the union equals the unsharded transform."""
     port = _free_port()
     ret = mp.Manager().dict()
-    mp.spawn(_worker_tiled, args=(world, port, n, ntaps, tile, ret), nprocs=world, join=True)
+    mp.spawn(_worker_tiled, args=(world, port, n, ntaps, tile, ret, in_place), nprocs=world, join=True)
     for r in range(world):
         err, done, n_local, order = ret[r]
         assert err < 1e-9, (r, err)
