@@ -116,3 +116,32 @@ def test_analog_signal_array_adapter():
     asa.n_signals = 2
     with pytest.raises(ValueError):
         standardize_input(asa)
+
+
+def test_constructor_validation_of_the_extensions():
+    """dtype / output / band_tol are checked before any device is touched."""
+    import pytest
+    from ghost_b200 import ContinuousWaveletTransform
+    with pytest.raises(ValueError):
+        ContinuousWaveletTransform(dtype=np.int32)
+    with pytest.raises(ValueError):
+        ContinuousWaveletTransform(output="phase")
+    with pytest.raises(ValueError):
+        ContinuousWaveletTransform(band_tol=-1e-7)
+    cwt = ContinuousWaveletTransform(dtype=np.float32, guard=False, guard_tol=1e-6, band_tol=2e-7)
+    assert cwt.amplitude is None and cwt.power is None and cwt.frequencies is None
+
+
+def test_time_shard_buffer_layout():
+    import torch
+    from ghost_b200 import sharding
+    sh = sharding.TimeShard(3, 100, 7, dtype=torch.float64)
+    assert sh.buf.shape == (3, 114) and sh.core.shape == (3, 100)
+    sh.core.fill_(1.0)
+    assert float(sh.buf[:, :7].abs().sum()) == 0.0 and float(sh.buf[:, 107:].abs().sum()) == 0.0
+    assert sh.core.data_ptr() == sh.buf.data_ptr() + 7 * 8
+    sharding.check_time_shards([100, 100, 50], 50)
+    import pytest
+    with pytest.raises(ValueError, match="halo"):
+        sharding.check_time_shards([100, 100, 49], 50)
+    sharding.check_time_shards([30], 50)                       # a single shard needs no halo
