@@ -1909,7 +1909,7 @@ static int fast_run(gcwt_plan* p, const TIn* x, int in_type, int64_t n_channels,
         prm.pow = guard ? p->d_guard_pow : nullptr; prm.pow_stride = p->n_scales;
         // the guard measures every guard_every-th chunk of a long segment (block-uniform choice in the kernels)
         auto set_guard_sampling = [&](int64_t n_chunks, int every, double chunk_to_rate) {
-            prm.guard_every = n_chunks >= 256 ? every : (n_chunks >= 64 ? every / 2 : 1);
+            prm.guard_every = n_chunks >= 512 ? 2 * every : (n_chunks >= 256 ? every : (n_chunks >= 64 ? every / 2 : 1));
             const double w = (double)n_chunks / (double)((n_chunks + prm.guard_every - 1) / prm.guard_every);
             prm.pow_weight = (float)w;
             // chunk energy -> energy of the segment at the full rate: D samples per decimated one, chunks overlap
